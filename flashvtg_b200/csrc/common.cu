@@ -1,0 +1,86 @@
+#include "common.cuh"
+
+namespace fvtg {
+
+HostState& host_state() {
+  static thread_local HostState s = {{0}, 0};
+  return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(host_state().err, sizeof(host_state().err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_arch() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(FVTG_EARCH, "no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return fail(FVTG_EARCH, "flashvtg_b200 needs an sm_100 device, found sm_%d%d", major, minor);
+  return FVTG_OK;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                   uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(FVTG_ELAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((pitch_elems * 2) & 15))
+    return fail(FVTG_EINVAL, "TMA operand must be 16-byte aligned with a 16-byte pitch");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FVTG_ELAUNCH, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu pitch=%llu",
+                (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                (unsigned long long)pitch_elems);
+  return FVTG_OK;
+}
+
+}  // namespace fvtg
+
+extern "C" {
+
+const char* fvtg_last_error(void) { return fvtg::host_state().err; }
+int64_t fvtg_last_launch_count(void) { return fvtg::host_state().launches; }
+int32_t fvtg_abi_version(void) { return FVTG_ABI_VERSION; }
+}

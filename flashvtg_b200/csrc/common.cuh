@@ -1,0 +1,79 @@
+// Host-side plumbing shared by every translation unit: error string, launch
+// counter, the TMA tensor-map encoder (driver entry point fetched at run time,
+// so the library links against cudart only) and the row-space geometry structs
+// that host code and kernels agree on.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/flashvtg_b200.h"
+
+namespace fvtg {
+
+typedef __nv_bfloat16 bf16;
+
+// -------------------------------------------------------------- host state --
+struct HostState {
+  char err[512];
+  int64_t launches;
+};
+HostState& host_state();
+
+int fail(int code, const char* fmt, ...);
+inline void count_launch(int n = 1) { host_state().launches += n; }
+
+#define FVTG_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return fvtg::fail(FVTG_ELAUNCH, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                            \
+  } while (0)
+
+#define FVTG_TRY(expr)             \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != FVTG_OK) return _rc; \
+  } while (0)
+
+#define FVTG_LAUNCH_CHECK(name)                                                        \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess)                                                             \
+      return fvtg::fail(FVTG_ELAUNCH, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    fvtg::count_launch();                                                              \
+  } while (0)
+
+int check_arch();  // FVTG_OK iff the current device is sm_100
+int sm_count();
+
+// 2-D bf16 tensor map: global [rows][cols] with row pitch `pitch_elems`, box
+// {box_cols (<=64 -> 128 B, SWIZZLE_128B), box_rows}.  Out-of-bounds elements
+// (including negative row coordinates) are zero-filled.
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                   uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols);
+
+// ----------------------------------------------------- row-space geometry --
+// Per-chunk geometry of the pyramid / head row spaces (DESIGN.md "row spaces").
+//   chain space, step j : video b owns rows [b*(P0>>j), (b+1)*(P0>>j)), first (len_b>>j) valid
+//   H1 (per-level gaps) : video b owns PH1 rows; level l at offset o1[l], then >= pad zero rows
+//   H2 (concatenated)   : video b owns PH2 rows; `pad` zeros, then the N_b points, then zeros
+struct PyrGeo {
+  int nlev;     // levels present at the batch's padded Lv
+  int pad;      // zero rows each head conv needs on both sides (max(head_k, coord_k) / 2)
+  int P0;       // chain pitch at step 0: Lv rounded up to a multiple of 2^(nlev-1) (and 8)
+  int PH1, PH2;
+  int n_max;    // sum_l (Lv >> l)
+  int o1[FVTG_MAX_LEVELS];
+  const int* vlen;  // [Bc] true video lengths of this chunk
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace fvtg
