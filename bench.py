@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py - videos/sec of the FlashVTG inference hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the whole hot path (input projections -> dummy encoder -> T2V cross-attention
+-> encoder -> saliency -> pyramid -> heads -> ASR -> decode -> top-k -> post-process -> NMS) over
+one batch of 1024 synthetic QVHighlights-InternVideo2-shape videos (BASELINE config #2) per GPU.
+For N > 1 it runs under torchrun, one rank per GPU, videos sharded by rank (no data-path collective
+until the final all-gather of the ranked spans); value = videos all ranks processed / max-over-ranks
+device time.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from flashvtg_b200 import synth  # noqa: E402
+from flashvtg_b200.config import PRESETS, gemm_flops_per_video  # noqa: E402
+
+METRIC = "videos/sec FlashVTG fwd (QVH shape)"
+UNIT = "videos/s"
+PRESET = "qvh_iv2"
+B_PER_GPU, LV, LT = 1024, 75, 32
+
+
+def workload_config(n_gpus):
+    return {"workload": "QVHighlights InternVideo2 shape (75 clips x 770-d video, 32 x 4096-d text), "
+                        "random-init FlashVTG (6 t2v / 3 enc / 2 dummy layers, 40 dummies, strides 1-16), "
+                        "fwd + ASR + decode + top-50 + post-process + NMS(0.7)",
+            "preset": PRESET, "videos_per_gpu_per_step": B_PER_GPU, "global_videos_per_step":
+            B_PER_GPU * n_gpus, "Lv": LV, "Lt": LT, "parallelism": f"video-sharded x{n_gpus}",
+            "l2_policy": "inputs larger than L2 (773 MB fp32 features per step per GPU vs 126 MB L2)"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_reference_pass(sd, cfg, batch, n):
+    """The oracle port of the reference path on n videos: bs=1 forwards (the reference's only
+    inference mode, model.py:248) + compose + PostProcessorDETR + post_processing_mr_nms."""
+    from flashvtg_b200.config import postprocessor_preset
+    from oracle import forward as O
+    from oracle import postproc as P
+    clip_ts, mn, mx, rnd = postprocessor_preset(cfg)
+    sub = {k: v[:n] for k, v in batch.items()}
+    t0 = time.perf_counter()
+    outs = O.forward_batch(sd, cfg, sub)
+    for b, o in enumerate(outs):
+        P.full_postproc(o["boundary"].numpy(), float(sub["duration"][b]), cfg.clip_length, clip_ts,
+                        mn, mx, rnd, cfg.nms_thd, cfg.nms_type)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = PRESETS[PRESET]
+    sd = synth.make_state_dict(cfg, 2024)
+    n = 32
+    batch = synth.make_inputs(cfg, n, LV, LT, seed=1234)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(sd, cfg, batch, min(n, 8))
+    ts = [cpu_reference_pass(sd, cfg, batch, n) for _ in range(args.steps)]
+    tot = sum(ts)
+    v = n * args.steps / tot
+    sample = (f"{n} videos per step (of the {B_PER_GPU}-video workload), bs=1 loop, fp32, "
+              f"torch.set_num_threads({cores})")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from flashvtg_b200 import _lib
+    from flashvtg_b200.model import FlashVTGB200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = PRESETS[PRESET]
+    sd = synth.make_state_dict(cfg, 2024)
+    model = FlashVTGB200(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    lib = _lib.load()
+
+    # distinct videos per rank: 64 generated ones tiled to the batch (numpy generation of 1024
+    # x 755 KB would dominate start-up); every video still streams its own bytes from HBM.
+    base = synth.make_inputs(cfg, 64, LV, LT, seed=1234 + rank)
+    rep = B_PER_GPU // 64
+    host = {k: v.repeat(rep, *([1] * (v.dim() - 1))).contiguous().pin_memory()
+            for k, v in base.items()}
+    d_in = {k: v.to(dev) for k, v in host.items()}
+    B = B_PER_GPU
+
+    def step_device():
+        r = model.infer(d_in["src_vid"], d_in["vid_len"], d_in["src_txt"], d_in["txt_len"],
+                        duration=d_in["duration"], nms="normal")
+        if world > 1:
+            # the only collective of the path: gather the ranked spans of every shard
+            gw = torch.empty(world * B, cfg.max_num_moment, 3, device=dev)
+            dist.all_gather_into_tensor(gw, r.nms_windows)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r = step_device()
+    barrier()
+    launches_per_step = r.launches + (1 if world > 1 else 0)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: same metric through the public API with HOST buffers (H2D + D2H inside) ----------
+    out_host = {k: torch.empty(s, dtype=dt).pin_memory() for k, s, dt in (
+        ("nms_windows", (B, cfg.max_num_moment, 3), torch.float32),
+        ("count", (B,), torch.int32), ("saliency", (B, LV), torch.float32))}
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        rr = model.infer(d["src_vid"], d["vid_len"], d["src_txt"], d["txt_len"],
+                         duration=d["duration"], nms="normal")
+        out_host["nms_windows"].copy_(rr.nms_windows, non_blocking=True)
+        out_host["count"].copy_(rr.count, non_blocking=True)
+        out_host["saliency"].copy_(rr.saliency, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the result on the host
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    k2 = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(k2):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    e2e = {"value": world * B * k2 / (ms2 * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
+           "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
+           "steps": k2, "ms_per_step": ms2 / k2}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): live CUDA-event timing per launch -----
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        lib.fvtg_prof_enable(1)
+        ksteps = max(2, min(args.steps, 5))
+        for _ in range(ksteps):
+            model.infer(d_in["src_vid"], d_in["vid_len"], d_in["src_txt"], d_in["txt_len"],
+                        duration=d_in["duration"], nms="normal")
+        torch.cuda.synchronize()
+        n_cls = len(_lib.PROF_CLASSES)
+        ms_c = (C.c_double * n_cls)()
+        ln_c = (C.c_int64 * n_cls)()
+        _lib.check(lib.fvtg_prof_collect(ms_c, ln_c, n_cls), "fvtg_prof_collect")
+        lib.fvtg_prof_enable(0)
+        pk, pk_kind = peaks()
+        flops_step = gemm_flops_per_video(cfg, LV, LT) * B
+        gemm_ms = ms_c[0] / ksteps
+        gemm_launches = ln_c[0] // ksteps
+        achieved = flops_step / (gemm_ms * 1e-3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        roof = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05/TMEM + TMA, fused epilogues)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_kind": pk_kind + " (cuBLAS bf16 sustained)", "traffic": None,
+                "launches_per_step": int(gemm_launches), "avg_launch_us": 1e3 * gemm_ms / max(gemm_launches, 1),
+                "algorithmic_gflop_per_video": gemm_flops_per_video(cfg, LV, LT) / 1e9,
+                "class_ms_per_step": {n: ms_c[i] / ksteps for i, n in enumerate(_lib.PROF_CLASSES)},
+                "class_launches_per_step": {n: int(ln_c[i] // ksteps)
+                                            for i, n in enumerate(_lib.PROF_CLASSES)},
+                "hbm_input_gbs": e2e["h2d_bytes_per_step"] / (ms / args.steps * 1e-3) / 1e9}
+        # ---- CPU baseline: the oracle port on a bounded sample, on this box's host cores -------
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n = 32
+            cb = {k: v[:n].clone() for k, v in base.items()}
+            cpu_reference_pass(sd, cfg, cb, 4)
+            tot, done = 0.0, 0
+            while tot < 10.0 and done < 16 * n:
+                tot += cpu_reference_pass(sd, cfg, cb, n)
+                done += n
+            cpu_base = {"value": done / tot, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{done} videos ({n} distinct) of the {B}-video workload, bs=1 "
+                                  f"loop of the oracle port, fp32, {cores} torch threads, {tot:.1f} s"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches_per_step * args.steps), "roofline": roof,
+                "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when invoked plainly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+               os.environ.get("MASTER_PORT", "29531"), os.path.abspath(__file__), "--gpus",
+               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

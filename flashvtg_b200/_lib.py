@@ -18,6 +18,7 @@ MAX_LEVELS = 8
 MAX_CONVS = 4
 MAX_MLP = 8
 MAX_TOPK = 64
+PROF_CLASSES = ("gemm", "attention", "ln_cast", "decode_nms", "other")
 
 NMS_NONE, NMS_NORMAL, NMS_LINEAR, NMS_HULL = -1, 0, 1, 2
 
@@ -88,9 +89,10 @@ class FvtgHeadsOut(C.Structure):
 
 
 class FvtgDecodeParams(C.Structure):
-    _fields_ = [("x", f32), ("clip_len", f32), ("topk", i32), ("num_levels", i32),
-                ("clip_ts", i32), ("min_ts", f32), ("max_ts", f32), ("round_multiple", i32),
-                ("nms_mode", i32), ("nms_thd", f32), ("max_after_nms", i32), ("_pad", i32)]
+    _fields_ = [("nms_thd", C.c_double), ("x", f32), ("clip_len", f32), ("inv_clip_len", f32),
+                ("min_ts", f32), ("max_ts", f32), ("topk", i32), ("num_levels", i32),
+                ("clip_ts", i32), ("round_multiple", i32), ("nms_mode", i32),
+                ("max_after_nms", i32), ("_pad", i32)]
 
 
 class FvtgDecodeOut(C.Structure):
@@ -108,13 +110,15 @@ SIGNATURES = {
                                      C.POINTER(FvtgHeadsOut), vp, C.c_size_t, vp]),
     "fvtg_decode_nms": (i32, [C.POINTER(FvtgDecodeParams), i32, i32, i32, vp, vp, vp, vp, vp,
                               C.POINTER(FvtgDecodeOut), vp]),
-    "fvtg_temporal_nms": (i32, [vp, vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]),
+    "fvtg_temporal_nms": (i32, [vp, vp, i32, i32, C.c_double, i32, i32, vp, vp, vp, vp]),
     "fvtg_forward": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgWeights), C.POINTER(FvtgBatch), vp,
                            C.POINTER(FvtgDecodeParams), C.POINTER(FvtgFusionOut),
                            C.POINTER(FvtgHeadsOut), C.POINTER(FvtgDecodeOut), vp, C.c_size_t, vp]),
     "fvtg_last_launch_count": (C.c_int64, []),
     "fvtg_last_error": (C.c_char_p, []),
     "fvtg_abi_version": (i32, []),
+    "fvtg_prof_enable": (None, [i32]),
+    "fvtg_prof_collect": (i32, [vp, vp, i32]),
     "fvtg_dbg_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
 }
 

@@ -136,3 +136,29 @@ def postprocessor_preset(cfg: ModelConfig):
             return True, 0.0, 360.0, True
         return True, 0.0, 150.0, True
     return False, 0.0, 50000.0, True
+
+
+def gemm_flops_per_video(cfg: ModelConfig, lv: int, lt: int) -> float:
+    """Algorithmic FLOPs (2 x MAC, unpadded dims) of the dense d_model contractions of one video -
+    every nn.Linear / Conv of the path, i.e. what
+    the tcgen05 GEMM kernel computes.  Excludes the per-head attention bmm's (attention kernel)
+    and the saliency head (mat-vec kernel).  QVH-IV2 (75, 32): 1.572e9 (of the 1.634e9 total FlopCounterMode reports)."""
+    d, ff = 256, 1024
+    s = cfg.num_dummies + lt
+    mac = lv * (cfg.v_feat_dim * d + d * d) + lt * (cfg.t_feat_dim * d + d * d)
+    sa = 3 * d * d + d * d + 2 * d * ff
+    mac += cfg.dummy_layers * s * sa
+    mac += cfg.t2v_layers * lv * (d * d + 2 * d * ff)
+    mac += cfg.enc_layers * lv * sa
+    n = 0
+    for l in range(cfg.num_levels):
+        if lv < (1 << l):
+            continue
+        n += lv >> l
+        for j in range(1, l + 1):
+            mac += (lv >> j) * 2 * d * d
+    k = cfg.kernel_size
+    head = cfg.num_conv_layers * k * d * d + d * 128 + (cfg.num_mlp_layers - 2) * 128 * 128 + 128
+    mac += 2 * n * head
+    mac += n * (cfg.coord_kernel * d * d + cfg.coord_kernel * d * 2)
+    return 2.0 * mac

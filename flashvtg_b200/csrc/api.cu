@@ -1,0 +1,605 @@
+// C-ABI entry points: validate, carve the caller's workspace, and enqueue the kernel sequence of
+// the hot path on the caller's stream, chunk by chunk (a chunk = the videos whose activations fit
+// the 126 MB L2, so only the raw features and the few-KB results touch HBM).
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace fvtg {
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+static int levels_present(const FvtgCfg& c, int Lv) {
+  int n = 0;
+  for (int l = 0; l < c.num_levels; ++l)
+    if (Lv >= (1 << l)) ++n;
+  return n;
+}
+
+static PyrGeo make_geo(const FvtgCfg& c, int Lv, const int* vlen) {
+  PyrGeo g;
+  memset(&g, 0, sizeof(g));
+  g.nlev = levels_present(c, Lv);
+  const int hk = c.head_k / 2, ck = c.coord_k / 2;
+  g.pad = hk > ck ? hk : ck;
+  const int align = 1 << (g.nlev > 4 ? g.nlev - 1 : 3);  // >= 8 rows keeps [rows/2][512] views 16B-pitched
+  g.P0 = round_up(Lv, align);
+  int o = g.pad, n = 0;
+  for (int l = 0; l < g.nlev; ++l) {
+    g.o1[l] = o;
+    o += (Lv >> l) + g.pad;
+    n += Lv >> l;
+  }
+  g.PH1 = o;
+  g.n_max = n;
+  g.PH2 = g.pad + n + g.pad;
+  g.vlen = vlen;
+  return g;
+}
+
+// Bump allocator over the caller's workspace; with base == nullptr it only measures.
+struct Carver {
+  uint8_t* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t count) {
+    off = round_up_sz(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct Ws {
+  // fusion
+  bf16 *vid_b, *txt_b, *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
+  float *Xf, *Yf, *pos_v, *pos_d, *tsum;
+  // pyramid + heads
+  bf16 *chain0, *chainA, *chainB, *H1, *H2, *hA, *hB, *mA, *mB;
+  // per-chunk head logits when the caller does not want them
+  float *cls, *conf, *coord;
+  size_t h1_rows, h2_rows;
+};
+
+static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws* w) {
+  Carver k{base, 0};
+  const size_t S = c.num_dummies + Lt;
+  const size_t Rv = static_cast<size_t>(Bc) * Lv, Rt = static_cast<size_t>(Bc) * Lt, Rs = Bc * S;
+  const size_t Rmax = Rv > Rs ? Rv : Rs;
+  PyrGeo g = make_geo(c, Lv, nullptr);
+  Ws t;
+  t.vid_b = k.take<bf16>(Rv * c.v_dim_pad);
+  t.txt_b = k.take<bf16>(Rt * c.t_dim_pad);
+  t.tmp256 = k.take<bf16>(Rmax * 256);
+  t.Xf = k.take<float>(Rs * 256);
+  t.Xb = k.take<bf16>(Rs * 256);
+  t.XPb = k.take<bf16>(Rs * 256);
+  t.Kc = k.take<bf16>(Rs * 256);
+  t.Yf = k.take<float>(Rv * 256);
+  t.Yb = k.take<bf16>(Rv * 256);
+  t.YPb = k.take<bf16>(Rv * 256);
+  t.pos_v = k.take<float>(Rv * 256);
+  t.pos_d = k.take<float>(S * 256);
+  t.qkv = k.take<bf16>(Rmax * 768);
+  t.att = k.take<bf16>(Rmax * 256);
+  t.ffh = k.take<bf16>(Rmax * 1024);
+  t.tsum = k.take<float>(8 * Rv);
+  const size_t Rc = static_cast<size_t>(Bc) * g.P0;
+  t.chain0 = k.take<bf16>(Rc * 256);
+  t.chainA = k.take<bf16>(Rc / 2 * 256 + 256);
+  t.chainB = k.take<bf16>(Rc / 4 * 256 + 256);
+  t.h1_rows = static_cast<size_t>(Bc) * g.PH1;
+  t.h2_rows = static_cast<size_t>(Bc) * g.PH2;
+  const size_t Rh = t.h1_rows > t.h2_rows ? t.h1_rows : t.h2_rows;
+  t.H1 = k.take<bf16>(t.h1_rows * 256);
+  t.H2 = k.take<bf16>(t.h2_rows * 256);
+  t.hA = k.take<bf16>(Rh * 256);
+  t.hB = k.take<bf16>(Rh * 256);
+  t.mA = k.take<bf16>(Rh * 128);
+  t.mB = k.take<bf16>(Rh * 128);
+  t.cls = k.take<float>(static_cast<size_t>(Bc) * g.n_max);
+  t.conf = k.take<float>(static_cast<size_t>(Bc) * g.n_max);
+  t.coord = k.take<float>(static_cast<size_t>(Bc) * g.n_max * 2);
+  if (w) *w = t;
+  return round_up_sz(k.off, 256);
+}
+
+static int chunk_videos(const FvtgCfg& c, int Lv, int Lt) {
+  const int forced = env_int("FVTG_CHUNK", 0);
+  if (forced > 0) return forced;
+  // One wave of 128-row tiles over the SMs for the N=256 GEMMs (the most frequent shape), and at
+  // most ~96 MB of per-chunk activations so the chunk stays L2 resident.
+  int sms = 148;
+  int bc = (sms * GEMM_BM) / (Lv > 0 ? Lv : 1);
+  if (bc < 1) bc = 1;
+  const size_t per_video = carve(c, 1, Lv, Lt, nullptr, nullptr);
+  const size_t budget = static_cast<size_t>(env_int("FVTG_L2_MB", 160)) << 20;
+  while (bc > 1 && per_video * bc > budget) bc = (bc * 3) / 4;
+  return bc;
+}
+
+static int check_cfg(const FvtgCfg* c) {
+  if (!c) return fail(FVTG_EINVAL, "null cfg");
+  if (c->abi_version != FVTG_ABI_VERSION) return fail(FVTG_EINVAL, "cfg.abi_version mismatch");
+  if (c->v_dim < 1 || c->t_dim < 1 || c->v_dim_pad % 64 || c->t_dim_pad % 64 ||
+      c->v_dim_pad < c->v_dim || c->t_dim_pad < c->t_dim)
+    return fail(FVTG_EINVAL, "cfg: feature dims must be padded to multiples of 64");
+  if (c->num_dummies < 1 || c->num_dummies > 256) return fail(FVTG_EINVAL, "cfg: num_dummies");
+  if (c->dummy_layers < 1 || c->dummy_layers > FVTG_MAX_LAYERS || c->t2v_layers < 0 ||
+      c->t2v_layers > FVTG_MAX_LAYERS || c->enc_layers < 0 || c->enc_layers > FVTG_MAX_LAYERS)
+    return fail(FVTG_EINVAL, "cfg: dummy_layers 1..%d, t2v/enc layers 0..%d", FVTG_MAX_LAYERS, FVTG_MAX_LAYERS);
+  if (c->num_levels < 1 || c->num_levels > FVTG_MAX_LEVELS) return fail(FVTG_EINVAL, "cfg: num_levels");
+  if (c->head_k < 1 || c->head_k > 7 || !(c->head_k & 1) || c->coord_k != 3)
+    return fail(FVTG_EINVAL, "cfg: head_k must be odd <= 7 and coord_k == 3");
+  if (c->num_conv_layers < 1 || c->num_conv_layers > FVTG_MAX_CONVS || c->num_mlp_layers < 2 ||
+      c->num_mlp_layers > FVTG_MAX_MLP)
+    return fail(FVTG_EINVAL, "cfg: num_conv_layers 1..4, num_mlp_layers 2..8");
+  return FVTG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One post-norm self-attention layer (transformer.py:408-421) over `rows` = B * L stream rows.
+static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, int Lseq, float* xf,
+                    bf16* xb, bf16* xpb, const float* pos, int pos_mod, const int* klen_src,
+                    int kbase, bf16* pos_extra, int pos_extra_rowlim) {
+  const int rows = B * Lseq;
+  {  // Q,K from x+pos ; V from x  (in_proj rows 0:512 / 512:768)
+    GemmArgs g = gemm_args(rows, 768, 256, 256);
+    g.a_switch_ntile = 2;
+    g.epi.mode = EPI_TILE;
+    g.epi.bias = L.in_proj.b;
+    g.epi.out = w.qkv;
+    g.epi.ld_out = 768;
+    FVTG_TRY(launch_gemm(st, xpb, xb, rows, 256, 256, L.in_proj.w, g));
+  }
+  {
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = w.qkv; a.ldq = 768;
+    a.k = w.qkv + 256; a.ldk = 768;
+    a.v = w.qkv + 512; a.ldv = 768;
+    a.out = w.att;
+    a.B = B; a.Lq = Lseq; a.Lk = Lseq;
+    a.klen_src = klen_src; a.kbase = kbase; a.v_first = 0; a.tsum = nullptr;
+    FVTG_TRY(launch_attention(st, a));
+  }
+  {  // x1 = LN1(x + att Wo^T + bo)
+    GemmArgs g = gemm_args(rows, 256, 256, 256);
+    g.epi.mode = EPI_ROW;
+    g.epi.bias = L.out_proj.b;
+    g.epi.res = xf;
+    g.epi.gamma = L.norm1.g; g.epi.beta = L.norm1.b;
+    g.epi.out_f32 = xf;
+    g.epi.out_bf16 = xb;
+    FVTG_TRY(launch_gemm(st, w.att, nullptr, rows, 256, 256, L.out_proj.w, g));
+  }
+  {  // h = PReLU(x1 W1^T + b1)
+    GemmArgs g = gemm_args(rows, 1024, 256, 256);
+    g.epi.mode = EPI_TILE;
+    g.epi.bias = L.ff1.b;
+    g.epi.act = ACT_PRELU; g.epi.prelu = L.prelu;
+    g.epi.out = w.ffh; g.epi.ld_out = 1024;
+    FVTG_TRY(launch_gemm(st, xb, nullptr, rows, 256, 256, L.ff1.w, g));
+  }
+  {  // x = LN2(x1 + h W2^T + b2) ; also bf16(x + pos) for the next layer's q/k
+    GemmArgs g = gemm_args(rows, 256, 256, 1024);
+    g.epi.mode = EPI_ROW;
+    g.epi.bias = L.ff2.b;
+    g.epi.res = xf;
+    g.epi.gamma = L.norm2.g; g.epi.beta = L.norm2.b;
+    g.epi.out_f32 = xf;
+    g.epi.out_bf16 = xb;
+    g.epi.out_bf16_pos = xpb;
+    g.epi.pos = pos; g.epi.pos_mod = pos_mod;
+    if (pos_extra) {  // last dummy layer: bf16(dummy + dummy_pos) rows go straight into Kc
+      g.epi.out_bf16_pos = pos_extra;
+      g.epi.pos_rowlim = pos_extra_rowlim;
+    }
+    FVTG_TRY(launch_gemm(st, w.ffh, nullptr, rows, 1024, 1024, L.ff2.w, g));
+  }
+  return FVTG_OK;
+}
+
+// One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396).
+static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, const Ws& w, int B,
+                     int Lv, int S, const int* tlen) {
+  const int rows = B * Lv;
+  {
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = w.YPb; a.ldq = 256;
+    a.k = w.Kc; a.ldk = 256;
+    a.v = w.Kc; a.ldv = 256;
+    a.out = w.att;
+    a.B = B; a.Lq = Lv; a.Lk = S;
+    a.klen_src = tlen; a.kbase = c.num_dummies; a.v_first = c.num_dummies;
+    a.tsum = w.tsum;
+    FVTG_TRY(launch_attention(st, a));
+  }
+  {  // z = y + att Wo^T + bo (kept fp32 as the residual) ; tmp256 = bf16(LN1(z))
+    GemmArgs g = gemm_args(rows, 256, 256, 256);
+    g.epi.mode = EPI_ROW;
+    g.epi.bias = L.out_proj.b;
+    g.epi.res = w.Yf;
+    g.epi.gamma = L.norm1.g; g.epi.beta = L.norm1.b;
+    g.epi.f32_preln = 1;
+    g.epi.out_f32 = w.Yf;
+    g.epi.out_bf16 = w.tmp256;
+    FVTG_TRY(launch_gemm(st, w.att, nullptr, rows, 256, 256, L.out_proj.w, g));
+  }
+  {
+    GemmArgs g = gemm_args(rows, 1024, 256, 256);
+    g.epi.mode = EPI_TILE;
+    g.epi.bias = L.ff1.b;
+    g.epi.act = ACT_PRELU; g.epi.prelu = L.prelu;
+    g.epi.out = w.ffh; g.epi.ld_out = 1024;
+    FVTG_TRY(launch_gemm(st, w.tmp256, nullptr, rows, 256, 256, L.ff1.w, g));
+  }
+  {  // y = LN2(z + h W2^T + b2)
+    GemmArgs g = gemm_args(rows, 256, 256, 1024);
+    g.epi.mode = EPI_ROW;
+    g.epi.bias = L.ff2.b;
+    g.epi.res = w.Yf;
+    g.epi.gamma = L.norm2.g; g.epi.beta = L.norm2.b;
+    g.epi.out_f32 = w.Yf;
+    g.epi.out_bf16 = w.Yb;
+    g.epi.out_bf16_pos = w.YPb;
+    g.epi.pos = w.pos_v;
+    FVTG_TRY(launch_gemm(st, w.ffh, nullptr, rows, 1024, 1024, L.ff2.w, g));
+  }
+  return FVTG_OK;
+}
+
+// LinearLayer x2 (model.py:99-110,782-789) for one modality.
+static int in_proj(cudaStream_t st, const FvtgInProj& P, const Ws& w, const float* src, bf16* stage,
+                   int rows, int dim, int dim_pad, GemmEpi final_epi) {
+  FVTG_TRY(launch_ln_cast(st, src, P.ln0.g, P.ln0.b, stage, rows, dim, dim_pad));
+  {  // tmp256 = bf16(LN1(relu(x W0^T + b0)))
+    GemmArgs g = gemm_args(rows, 256, 256, dim_pad);
+    g.epi.mode = EPI_ROW;
+    g.epi.bias = P.fc0.b;
+    g.epi.act = ACT_RELU;
+    g.epi.gamma = P.ln1.g; g.epi.beta = P.ln1.b;
+    g.epi.out_bf16 = w.tmp256;
+    FVTG_TRY(launch_gemm(st, stage, nullptr, rows, dim_pad, dim_pad, P.fc0.w, g));
+  }
+  {
+    GemmArgs g = gemm_args(rows, 256, 256, 256);
+    g.epi = final_epi;
+    g.epi.mode = EPI_ROW;
+    g.epi.bias = P.fc1.b;
+    FVTG_TRY(launch_gemm(st, w.tmp256, nullptr, rows, 256, 256, P.fc1.w, g));
+  }
+  return FVTG_OK;
+}
+
+static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W, const Ws& w,
+                        int B, int Lv, int Lt, const float* vid, const float* txt,
+                        const int* vlen, const int* tlen, float* video_emb, float* saliency,
+                        float* t2v, float* dummy_tokens) {
+  const int nd = c.num_dummies, S = nd + Lt;
+  FVTG_TRY(launch_posenc(st, w.pos_v, vlen, B, Lv));
+  FVTG_TRY(launch_fill_dummy(st, W.dummy_tok, W.dummy_pos, w.Xf, w.Xb, w.XPb, w.pos_d, B, S, nd));
+  FVTG_CUDA_OK(cudaMemsetAsync(w.tsum, 0, sizeof(float) * 8 * B * Lv, st));
+  count_launch();
+  {  // text: rows scattered into the [dummies ‖ text] stream, plus the constant text keys/values
+    GemmEpi e;
+    memset(&e, 0, sizeof(e));
+    e.rowmap = RM_TXT; e.rm_a = Lt; e.rm_b = S; e.rm_c = nd;
+    e.out_f32 = w.Xf; e.out_bf16 = w.Xb; e.out_bf16_pos = w.XPb; e.out_x1 = w.Kc;
+    FVTG_TRY(in_proj(st, W.txt, w, txt, w.txt_b, B * Lt, c.t_dim, c.t_dim_pad, e));
+  }
+  {  // video
+    GemmEpi e;
+    memset(&e, 0, sizeof(e));
+    e.out_f32 = w.Yf; e.out_bf16 = w.Yb; e.out_bf16_pos = w.YPb; e.pos = w.pos_v;
+    FVTG_TRY(in_proj(st, W.vid, w, vid, w.vid_b, B * Lv, c.v_dim, c.v_dim_pad, e));
+  }
+  for (int i = 0; i < c.dummy_layers; ++i) {
+    const bool last = i == c.dummy_layers - 1;
+    FVTG_TRY(sa_layer(st, W.dummy[i], w, B, S, w.Xf, w.Xb, w.XPb, w.pos_d, S, tlen, nd,
+                      last ? w.Kc : nullptr, nd));
+  }
+  if (dummy_tokens) {
+    FVTG_CUDA_OK(cudaMemcpy2DAsync(dummy_tokens, sizeof(float) * nd * 256, w.Xf,
+                                   sizeof(float) * S * 256, sizeof(float) * nd * 256, B,
+                                   cudaMemcpyDeviceToDevice, st));
+    count_launch();
+  }
+  for (int i = 0; i < c.t2v_layers; ++i) FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen));
+  for (int i = 0; i < c.enc_layers; ++i)
+    FVTG_TRY(sa_layer(st, W.enc[i], w, B, Lv, w.Yf, w.Yb, w.YPb, w.pos_v, 0, vlen, 0, nullptr, 0));
+  FVTG_TRY(launch_saliency(st, w.Yf, vlen, W.sal_w1, W.sal_b1, W.sal_w2t, W.sal_b2, w.tsum,
+                           c.t2v_layers > 0 ? c.t2v_layers : 1, saliency, t2v, B, Lv));
+  if (video_emb) {
+    FVTG_CUDA_OK(cudaMemcpyAsync(video_emb, w.Yf, sizeof(float) * B * Lv * 256,
+                                 cudaMemcpyDeviceToDevice, st));
+    count_launch();
+  }
+  return FVTG_OK;
+}
+
+static int score_head(cudaStream_t st, const FvtgCfg& c, const FvtgScoreHead& H, const Ws& w,
+                      const bf16* in, int rows, int rowmap, const PyrGeo& geo, float* out_logit) {
+  const int k = c.head_k;
+  const bf16* cur = in;
+  bf16* bufs[2] = {w.hA, w.hB};
+  for (int ci = 0; ci < c.num_conv_layers; ++ci) {
+    GemmArgs g = gemm_args(rows, 256, 256, 256);
+    g.ntaps = k;
+    g.kb_per_tap = 4;
+    for (int t = 0; t < k; ++t) g.tap_shift[t] = t - k / 2;
+    g.epi.mode = EPI_TILE;
+    g.epi.rowmap = rowmap;
+    g.epi.geo = geo;
+    g.epi.bias = H.conv[ci].b;
+    g.epi.act = ACT_RELU;
+    g.epi.out = bufs[ci & 1];
+    g.epi.ld_out = 256;
+    FVTG_TRY(launch_gemm(st, cur, nullptr, rows, 256, 256, H.conv[ci].w, g));
+    cur = bufs[ci & 1];
+  }
+  bf16* mb[2] = {w.mA, w.mB};
+  int kin = 256;
+  for (int m = 0; m < c.num_mlp_layers - 1; ++m) {
+    const bool last = m == c.num_mlp_layers - 2;
+    GemmArgs g = gemm_args(rows, 128, 128, kin);
+    g.epi.rowmap = rowmap;
+    g.epi.geo = geo;
+    g.epi.bias = H.mlp[m].b;
+    if (!last) {
+      g.epi.mode = EPI_TILE;
+      g.epi.act = ACT_RELU;
+      g.epi.out = mb[m & 1];
+      g.epi.ld_out = 128;
+    } else {
+      g.epi.mode = EPI_DOT;
+      g.epi.dotw = H.last_w;
+      g.epi.dotb = H.last_b;
+      g.epi.out_dot = out_logit;
+    }
+    FVTG_TRY(launch_gemm(st, cur, nullptr, rows, kin, kin, H.mlp[m].w, g));
+    cur = mb[m & 1];
+    kin = 128;
+  }
+  return FVTG_OK;
+}
+
+static int pyramid_heads_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W, const Ws& w,
+                               int B, int Lv, const float* F, const int* vlen, float* cls,
+                               float* conf, float* coord) {
+  PyrGeo geo = make_geo(c, Lv, vlen);
+  FVTG_CUDA_OK(cudaMemsetAsync(w.H1, 0, static_cast<size_t>(B) * geo.PH1 * 256 * sizeof(bf16), st));
+  FVTG_CUDA_OK(cudaMemsetAsync(w.H2, 0, static_cast<size_t>(B) * geo.PH2 * 256 * sizeof(bf16), st));
+  count_launch(2);
+  FVTG_TRY(launch_level0(st, F, w.chain0, w.H1, w.H2, B, Lv, geo));
+  // Temporal Feature Layering (blocks.py:52-70): level l = l strided convs from ReLU(F), own weights
+  for (int l = 1; l < geo.nlev; ++l) {
+    const bf16* src = w.chain0;
+    bf16* pp[2] = {w.chainA, w.chainB};
+    for (int j = 1; j <= l; ++j) {
+      const int rows_out = B * (geo.P0 >> j);
+      GemmArgs g = gemm_args(rows_out, 256, 256, 512);
+      g.epi.mode = EPI_ROW;
+      g.epi.rowmap = RM_CHAIN;
+      g.epi.rm_a = j; g.epi.rm_b = l; g.epi.rm_c = (j == l) ? 1 : 0;
+      g.epi.geo = geo;
+      g.epi.bias = W.pyr[l][j - 1].conv.b;
+      g.epi.gamma = W.pyr[l][j - 1].ln.g; g.epi.beta = W.pyr[l][j - 1].ln.b;
+      g.epi.post_relu = 1;
+      bf16* dst = pp[(j - 1) & 1];
+      g.epi.out_bf16 = (j == l) ? nullptr : dst;
+      g.epi.out_x1 = w.H1; g.epi.out_x2 = w.H2;
+      FVTG_TRY(launch_gemm(st, src, nullptr, rows_out, 512, 512, W.pyr[l][j - 1].conv.w, g));
+      src = dst;
+    }
+  }
+  FVTG_CUDA_OK(cudaMemsetAsync(cls, 0, sizeof(float) * B * geo.n_max, st));
+  FVTG_CUDA_OK(cudaMemsetAsync(conf, 0, sizeof(float) * B * geo.n_max, st));
+  FVTG_CUDA_OK(cudaMemsetAsync(coord, 0, sizeof(float) * B * geo.n_max * 2, st));
+  count_launch(3);
+  FVTG_TRY(score_head(st, c, W.cls, w, w.H1, B * geo.PH1, RM_H1, geo, cls));
+  FVTG_TRY(score_head(st, c, W.conf, w, w.H2, B * geo.PH2, RM_H2, geo, conf));
+  {  // coord head (blocks.py:90-105): conv k3 + ReLU, conv k3 -> 2, exp * coef[level]
+    const int rows = B * geo.PH1;
+    GemmArgs g = gemm_args(rows, 256, 256, 256);
+    g.ntaps = 3; g.kb_per_tap = 4;
+    for (int t = 0; t < 3; ++t) g.tap_shift[t] = t - 1;
+    g.epi.mode = EPI_TILE;
+    g.epi.rowmap = RM_H1; g.epi.geo = geo;
+    g.epi.bias = W.coord1.b;
+    g.epi.act = ACT_RELU;
+    g.epi.out = w.hA; g.epi.ld_out = 256;
+    FVTG_TRY(launch_gemm(st, w.H1, nullptr, rows, 256, 256, W.coord1.w, g));
+    GemmArgs h = gemm_args(rows, 16, 16, 256);
+    h.ntaps = 3; h.kb_per_tap = 4;
+    for (int t = 0; t < 3; ++t) h.tap_shift[t] = t - 1;
+    h.epi.mode = EPI_COORD;
+    h.epi.rowmap = RM_H1; h.epi.geo = geo;
+    h.epi.bias = W.coord2.b;
+    h.epi.out_coord = coord;
+    for (int l = 0; l < FVTG_MAX_LEVELS; ++l) h.epi.coef[l] = W.coef[l];
+    FVTG_TRY(launch_gemm(st, w.hA, nullptr, rows, 256, 256, W.coord2.w, h));
+  }
+  return FVTG_OK;
+}
+
+static FvtgDecodeParams default_decode(const FvtgCfg& c, const FvtgWeights& W) {
+  FvtgDecodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = W.x;
+  p.clip_len = c.clip_len;
+  p.inv_clip_len = static_cast<float>(1.0 / static_cast<double>(c.clip_len));
+  p.topk = c.max_num_moment;
+  p.num_levels = c.num_levels;
+  p.nms_mode = FVTG_NMS_NONE;
+  return p;
+}
+
+}  // namespace fvtg
+
+using namespace fvtg;
+
+extern "C" {
+
+size_t fvtg_workspace_bytes(const FvtgCfg* cfg, int32_t B, int32_t Lv, int32_t Lt) {
+  if (check_cfg(cfg) != FVTG_OK || B < 1 || Lv < 1 || Lt < 1) return 0;
+  int bc = chunk_videos(*cfg, Lv, Lt);
+  if (bc > B) bc = B;
+  return carve(*cfg, bc, Lv, Lt, nullptr, nullptr) + 1024;
+}
+
+int32_t fvtg_chunk_videos(const FvtgCfg* cfg, int32_t Lv, int32_t Lt) {
+  if (check_cfg(cfg) != FVTG_OK || Lv < 1 || Lt < 1) return 0;
+  return chunk_videos(*cfg, Lv, Lt);
+}
+
+static int prep_ws(const FvtgCfg* cfg, int B, int Lv, int Lt, void* workspace, size_t ws_bytes,
+                   int* bc_out, Ws* w) {
+  if (!workspace) return fail(FVTG_EINVAL, "null workspace");
+  int bc = chunk_videos(*cfg, Lv, Lt);
+  if (bc > B) bc = B;
+  uint8_t* base = reinterpret_cast<uint8_t*>(round_up_sz(reinterpret_cast<size_t>(workspace), 1024));
+  const size_t need = carve(*cfg, bc, Lv, Lt, base, w) + (base - reinterpret_cast<uint8_t*>(workspace));
+  if (need > ws_bytes)
+    return fail(FVTG_EWORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
+  *bc_out = bc;
+  return FVTG_OK;
+}
+
+static int check_shapes(const FvtgCfg* cfg, int B, int Lv, int Lt) {
+  if (B < 1 || Lv < 1 || Lt < 1) return fail(FVTG_EINVAL, "B, Lv, Lt must be positive");
+  if (Lv > 1024) return fail(FVTG_EINVAL, "Lv %d exceeds the 1024-clip buffer (generator.py:60)", Lv);
+  if (cfg->num_dummies + Lt > 1024) return fail(FVTG_EINVAL, "num_dummies + Lt too large");
+  return FVTG_OK;
+}
+
+int32_t fvtg_fusion_fwd(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* in,
+                        const FvtgFusionOut* out, void* workspace, size_t ws_bytes, void* stream) {
+  host_state().launches = 0;
+  FVTG_TRY(check_cfg(cfg));
+  if (!w || !in || !out || !in->vid || !in->txt || !in->vid_len || !in->txt_len || !out->saliency)
+    return fail(FVTG_EINVAL, "fusion_fwd: null argument");
+  FVTG_TRY(check_shapes(cfg, in->B, in->Lv, in->Lt));
+  FVTG_TRY(check_arch());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int bc = 0;
+  Ws ws;
+  FVTG_TRY(prep_ws(cfg, in->B, in->Lv, in->Lt, workspace, ws_bytes, &bc, &ws));
+  const int Lv = in->Lv, Lt = in->Lt, nd = cfg->num_dummies;
+  for (int b0 = 0; b0 < in->B; b0 += bc) {
+    const int nb = in->B - b0 < bc ? in->B - b0 : bc;
+    FVTG_TRY(fusion_chunk(
+        st, *cfg, *w, ws, nb, Lv, Lt, in->vid + static_cast<size_t>(b0) * Lv * cfg->v_dim,
+        in->txt + static_cast<size_t>(b0) * Lt * cfg->t_dim, in->vid_len + b0, in->txt_len + b0,
+        out->video_emb ? out->video_emb + static_cast<size_t>(b0) * Lv * 256 : nullptr,
+        out->saliency + static_cast<size_t>(b0) * Lv,
+        out->t2v ? out->t2v + static_cast<size_t>(b0) * Lv : nullptr,
+        out->dummy_tokens ? out->dummy_tokens + static_cast<size_t>(b0) * nd * 256 : nullptr));
+  }
+  return FVTG_OK;
+}
+
+int32_t fvtg_pyramid_heads_fwd(const FvtgCfg* cfg, const FvtgWeights* w, int32_t B, int32_t Lv,
+                               const float* video_emb, const int32_t* vid_len,
+                               const FvtgHeadsOut* out, void* workspace, size_t ws_bytes,
+                               void* stream) {
+  host_state().launches = 0;
+  FVTG_TRY(check_cfg(cfg));
+  if (!w || !video_emb || !vid_len || !out || !out->cls_logit || !out->conf_logit || !out->coord)
+    return fail(FVTG_EINVAL, "pyramid_heads_fwd: null argument");
+  FVTG_TRY(check_shapes(cfg, B, Lv, 1));
+  FVTG_TRY(check_arch());
+  PyrGeo g0 = make_geo(*cfg, Lv, nullptr);
+  if (out->n_max != g0.n_max)
+    return fail(FVTG_EINVAL, "pyramid_heads_fwd: n_max %d != %d for Lv %d", out->n_max, g0.n_max, Lv);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int bc = 0;
+  Ws ws;
+  FVTG_TRY(prep_ws(cfg, B, Lv, 1, workspace, ws_bytes, &bc, &ws));
+  for (int b0 = 0; b0 < B; b0 += bc) {
+    const int nb = B - b0 < bc ? B - b0 : bc;
+    FVTG_TRY(pyramid_heads_chunk(st, *cfg, *w, ws, nb, Lv,
+                                 video_emb + static_cast<size_t>(b0) * Lv * 256, vid_len + b0,
+                                 out->cls_logit + static_cast<size_t>(b0) * g0.n_max,
+                                 out->conf_logit + static_cast<size_t>(b0) * g0.n_max,
+                                 out->coord + static_cast<size_t>(b0) * g0.n_max * 2));
+  }
+  return FVTG_OK;
+}
+
+int32_t fvtg_decode_nms(const FvtgDecodeParams* p, int32_t B, int32_t Lv, int32_t n_max,
+                        const float* cls_logit, const float* conf_logit, const float* coord,
+                        const int32_t* vid_len, const float* duration, const FvtgDecodeOut* out,
+                        void* stream) {
+  host_state().launches = 0;
+  if (!p || !cls_logit || !conf_logit || !coord || !vid_len || !out)
+    return fail(FVTG_EINVAL, "decode_nms: null argument");
+  if (p->num_levels < 1 || p->num_levels > FVTG_MAX_LEVELS)
+    return fail(FVTG_EINVAL, "decode_nms: num_levels");
+  FVTG_TRY(check_arch());
+  return launch_decode_nms(static_cast<cudaStream_t>(stream), *p, B, Lv, n_max, cls_logit,
+                           conf_logit, coord, vid_len, duration, *out);
+}
+
+int32_t fvtg_temporal_nms(const float* windows, const int32_t* count, int32_t B, int32_t M,
+                          double thd, int32_t mode, int32_t max_after_nms, float* out_windows,
+                          int32_t* order, int32_t* out_count, void* stream) {
+  host_state().launches = 0;
+  if (!windows) return fail(FVTG_EINVAL, "temporal_nms: null windows");
+  FVTG_TRY(check_arch());
+  return launch_temporal_nms(static_cast<cudaStream_t>(stream), windows, count, B, M, thd, mode,
+                             max_after_nms, out_windows, order, out_count);
+}
+
+int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* in,
+                     const float* duration, const FvtgDecodeParams* dp, const FvtgFusionOut* fout,
+                     const FvtgHeadsOut* hout, const FvtgDecodeOut* dout, void* workspace,
+                     size_t ws_bytes, void* stream) {
+  host_state().launches = 0;
+  FVTG_TRY(check_cfg(cfg));
+  if (!w || !in || !fout || !dout || !in->vid || !in->txt || !in->vid_len || !in->txt_len ||
+      !fout->saliency)
+    return fail(FVTG_EINVAL, "forward: null argument");
+  FVTG_TRY(check_shapes(cfg, in->B, in->Lv, in->Lt));
+  FVTG_TRY(check_arch());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int bc = 0;
+  Ws ws;
+  FVTG_TRY(prep_ws(cfg, in->B, in->Lv, in->Lt, workspace, ws_bytes, &bc, &ws));
+  const int Lv = in->Lv, Lt = in->Lt, nd = cfg->num_dummies;
+  PyrGeo g0 = make_geo(*cfg, Lv, nullptr);
+  if (hout && hout->cls_logit && hout->n_max != g0.n_max)
+    return fail(FVTG_EINVAL, "forward: heads n_max %d != %d", hout->n_max, g0.n_max);
+  FvtgDecodeParams p = dp ? *dp : default_decode(*cfg, *w);
+  const bool keep_heads = hout && hout->cls_logit && hout->conf_logit && hout->coord;
+  for (int b0 = 0; b0 < in->B; b0 += bc) {
+    const int nb = in->B - b0 < bc ? in->B - b0 : bc;
+    FVTG_TRY(fusion_chunk(
+        st, *cfg, *w, ws, nb, Lv, Lt, in->vid + static_cast<size_t>(b0) * Lv * cfg->v_dim,
+        in->txt + static_cast<size_t>(b0) * Lt * cfg->t_dim, in->vid_len + b0, in->txt_len + b0,
+        fout->video_emb ? fout->video_emb + static_cast<size_t>(b0) * Lv * 256 : nullptr,
+        fout->saliency + static_cast<size_t>(b0) * Lv,
+        fout->t2v ? fout->t2v + static_cast<size_t>(b0) * Lv : nullptr,
+        fout->dummy_tokens ? fout->dummy_tokens + static_cast<size_t>(b0) * nd * 256 : nullptr));
+    float* cls = keep_heads ? hout->cls_logit + static_cast<size_t>(b0) * g0.n_max : ws.cls;
+    float* conf = keep_heads ? hout->conf_logit + static_cast<size_t>(b0) * g0.n_max : ws.conf;
+    float* coord = keep_heads ? hout->coord + static_cast<size_t>(b0) * g0.n_max * 2 : ws.coord;
+    FVTG_TRY(pyramid_heads_chunk(st, *cfg, *w, ws, nb, Lv, ws.Yf, in->vid_len + b0, cls, conf, coord));
+    FvtgDecodeOut d = *dout;
+    const int tk = p.topk;
+    if (d.boundary) d.boundary += static_cast<size_t>(b0) * tk * 3;
+    if (d.windows) d.windows += static_cast<size_t>(b0) * tk * 3;
+    if (d.nms_windows) d.nms_windows += static_cast<size_t>(b0) * tk * 3;
+    if (d.nms_order) d.nms_order += static_cast<size_t>(b0) * tk;
+    if (d.count) d.count += b0;
+    if (d.nms_count) d.nms_count += b0;
+    FVTG_TRY(launch_decode_nms(st, p, nb, Lv, g0.n_max, cls, conf, coord, in->vid_len + b0,
+                               duration ? duration + b0 : nullptr, d));
+  }
+  return FVTG_OK;
+}
+
+}  // extern "C"

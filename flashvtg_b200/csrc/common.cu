@@ -1,5 +1,7 @@
 #include "common.cuh"
 
+#include <vector>
+
 namespace fvtg {
 
 HostState& host_state() {
@@ -13,6 +15,41 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(host_state().err, sizeof(host_state().err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+struct ProfRec { cudaEvent_t a, b; int cls; };
+struct ProfState {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+};
+static ProfState& prof_state() {
+  static thread_local ProfState s;
+  return s;
+}
+bool prof_on() { return prof_state().on; }
+static cudaEvent_t prof_event() {
+  ProfState& p = prof_state();
+  if (!p.pool.empty()) {
+    cudaEvent_t e = p.pool.back();
+    p.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(cudaStream_t st, int cls) {
+  ProfRec r;
+  r.a = prof_event();
+  r.b = prof_event();
+  r.cls = cls;
+  cudaEventRecord(r.a, st);
+  prof_state().recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  ProfState& p = prof_state();
+  if (!p.recs.empty()) cudaEventRecord(p.recs.back().b, st);
 }
 
 int check_arch() {
@@ -83,4 +120,29 @@ extern "C" {
 const char* fvtg_last_error(void) { return fvtg::host_state().err; }
 int64_t fvtg_last_launch_count(void) { return fvtg::host_state().launches; }
 int32_t fvtg_abi_version(void) { return FVTG_ABI_VERSION; }
+
+void fvtg_prof_enable(int32_t on) { fvtg::prof_state().on = on != 0; }
+
+int32_t fvtg_prof_collect(double* ms, int64_t* launches, int32_t n_classes) {
+  using namespace fvtg;
+  ProfState& p = prof_state();
+  for (int i = 0; i < n_classes; ++i) {
+    if (ms) ms[i] = 0.0;
+    if (launches) launches[i] = 0;
+  }
+  for (ProfRec& r : p.recs) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) return fail(FVTG_ELAUNCH, "prof_collect: %s", cudaGetErrorString(e));
+    if (r.cls >= 0 && r.cls < n_classes) {
+      if (ms) ms[r.cls] += t;
+      if (launches) launches[r.cls] += 1;
+    }
+    p.pool.push_back(r.a);
+    p.pool.push_back(r.b);
+  }
+  p.recs.clear();
+  return FVTG_OK;
+}
 }

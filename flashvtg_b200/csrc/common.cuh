@@ -49,6 +49,21 @@ inline void count_launch(int n = 1) { host_state().launches += n; }
     fvtg::count_launch();                                                              \
   } while (0)
 
+// ------------------------------------------------------------- profiler --
+// Bench hook (fvtg_prof_enable / fvtg_prof_collect): when enabled every launcher brackets its
+// kernel with a CUDA event pair on the launching stream, so bench.py can time each kernel class
+// live (the roofline numerator) without a profiler attached.  Off by default: zero cost.
+enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LNCAST = 2, PC_DECODE = 3, PC_OTHER = 4, PC_COUNT = 5 };
+bool prof_on();
+void prof_begin(cudaStream_t st, int cls);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(cudaStream_t s, int cls) : st(s), on(prof_on()) { if (on) prof_begin(st, cls); }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 int check_arch();  // FVTG_OK iff the current device is sm_100
 int sm_count();
 

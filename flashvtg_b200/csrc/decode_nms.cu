@@ -1,0 +1,348 @@
+// Kernel group C: Adaptive Score Refinement mix, sigmoid, span decode, top-k, the host
+// post-processing chain (clamp / 4-decimal rounding / PostProcessorDETR) and temporal NMS,
+// one CTA per video.  Reference: FlashVTG/model.py:201,247-266; FlashVTG/inference.py:286-290;
+// FlashVTG/postprocessing.py:25-50; FlashVTG/inference.py:36-57; utils/temporal_nms.py:25-74.
+//
+// Everything that decides an index (sort keys, IoU, threshold compares) uses explicitly rounded
+// fp32 / fp64 operations (__fadd_rn ...; no FMA contraction) in the reference's operation order,
+// so NMS selection order and keep masks are bit-exact for identical inputs.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace fvtg {
+
+constexpr int DEC_THREADS = 256;
+constexpr int NMS_MAX = FVTG_MAX_TOPK;  // 64 rows
+
+struct NmsSmem {
+  float st[NMS_MAX], ed[NMS_MAX], sc[NMS_MAX];
+  int src[NMS_MAX];
+  float o_st[NMS_MAX], o_ed[NMS_MAX], o_sc[NMS_MAX];
+  int o_src[NMS_MAX];
+  int o_cnt;
+};
+
+__device__ __forceinline__ float round4_f32(float x) {
+  // float(f"{x:.4f}") then back to fp32 (torch.tensor(list)): x * 1e4 is exact in fp64.
+  return static_cast<float>(__ddiv_rn(rint(__dmul_rn(static_cast<double>(x), 1e4)), 1e4));
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  // torch.clamp: NaN propagates; min then max like at::clamp(min, max)
+  if (x != x) return x;
+  return fminf(fmaxf(x, lo), hi);
+}
+
+// a sorts strictly before b in a descending sort with NaN first and position as tie-break
+__device__ __forceinline__ bool sorts_before(float sa, int pa, float sb, int pb) {
+  const bool na = sa != sa, nb = sb != sb;
+  if (na != nb) return na;
+  if (!na && sa != sb) return sa > sb;
+  return pa < pb;
+}
+
+// post_processing_mr_nms on n <= 64 rows held in shared memory; executed by one full warp.
+// mode 0 normal / 1 linear.  Results in o_* (final order) and o_src (source row of each).
+__device__ void nms_f32_warp(NmsSmem& S, int n, float thd, int mode, int lane) {
+  for (int i = 0; i < n; ++i) {
+    // first argmax over rows [i, n): NaN counts as the maximum (torch.argmax)
+    float bv = 0.f;
+    int bi = 1 << 30;
+    bool bn = false;
+    for (int r = i + lane; r < n; r += 32) {
+      const float v = S.sc[r];
+      const bool vn = v != v;
+      bool take;
+      if (bi == (1 << 30)) take = true;
+      else if (vn != bn) take = vn;
+      else if (!vn && v != bv) take = v > bv;
+      else take = false;  // equal (or both NaN): keep the earlier index
+      if (take) { bv = v; bi = r; bn = vn; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const bool on = ov != ov;
+      bool take;
+      if (oi == (1 << 30)) take = false;
+      else if (bi == (1 << 30)) take = true;
+      else if (on != bn) take = on;
+      else if (!on && ov != bv) take = ov > bv;
+      else take = oi < bi;
+      if (take) { bv = ov; bi = oi; bn = on; }
+    }
+    if (lane == 0 && bi != i) {
+      float t;
+      int ti;
+      t = S.st[i]; S.st[i] = S.st[bi]; S.st[bi] = t;
+      t = S.ed[i]; S.ed[i] = S.ed[bi]; S.ed[bi] = t;
+      t = S.sc[i]; S.sc[i] = S.sc[bi]; S.sc[bi] = t;
+      ti = S.src[i]; S.src[i] = S.src[bi]; S.src[bi] = ti;
+    }
+    __syncwarp();
+    const float s0 = S.st[i], e0 = S.ed[i];
+    const float a0 = __fsub_rn(e0, s0);
+    for (int r = i + 1 + lane; r < n; r += 32) {
+      const float s1 = S.st[r], e1 = S.ed[r];
+      const float a1 = __fsub_rn(e1, s1);
+      float inter = __fsub_rn(fminf(e0, e1), fmaxf(s0, s1));
+      if (inter < 0.f) inter = 0.f;  // clamp(min=0), NaN stays NaN
+      const float uni = __fsub_rn(__fadd_rn(a0, a1), inter);
+      const float iou = __fdiv_rn(inter, uni);
+      if (mode == FVTG_NMS_NORMAL) {
+        if (iou >= thd) S.sc[r] = 0.f;  // NaN compares false: kept
+      } else {
+        S.sc[r] = __fmul_rn(S.sc[r], __fsub_rn(1.f, iou));
+      }
+    }
+    __syncwarp();
+  }
+  // final descending sort, stable by current position (rank by counting)
+  for (int r = lane; r < n; r += 32) {
+    const float s = S.sc[r];
+    int rank = 0;
+    for (int q = 0; q < n; ++q)
+      if (q != r && sorts_before(S.sc[q], q, s, r)) ++rank;
+    S.o_st[rank] = S.st[r]; S.o_ed[rank] = S.ed[r]; S.o_sc[rank] = s; S.o_src[rank] = S.src[r];
+  }
+  if (lane == 0) S.o_cnt = n;
+  __syncwarp();
+}
+
+// utils/temporal_nms.py on n <= 64 rows, fp64 arithmetic, one full warp.
+__device__ void nms_hull_warp(NmsSmem& S, int n, double thd, int max_after, int lane) {
+  if (n == 1) {
+    if (lane == 0) {
+      S.o_st[0] = S.st[0]; S.o_ed[0] = S.ed[0]; S.o_sc[0] = S.sc[0]; S.o_src[0] = S.src[0];
+      S.o_cnt = 1;
+    }
+    __syncwarp();
+    return;
+  }
+  // stable descending sort by score into o_* (python sorted(reverse=True) keeps input order on ties)
+  for (int r = lane; r < n; r += 32) {
+    const float s = S.sc[r];
+    int rank = 0;
+    for (int q = 0; q < n; ++q) {
+      const float sq = S.sc[q];
+      if (q != r && (sq > s || (sq == s && q < r))) ++rank;
+    }
+    S.o_st[rank] = S.st[r]; S.o_ed[rank] = S.ed[r]; S.o_sc[rank] = s; S.o_src[rank] = S.src[r];
+  }
+  __syncwarp();
+  unsigned long long dead = 0ull;
+  int alive = n, cnt = 0;
+  for (int a = 0; a < n; ++a) {
+    if ((dead >> a) & 1ull) continue;
+    if (cnt >= max_after) break;
+    if (alive > 1) {
+      const double s0 = S.o_st[a], e0 = S.o_ed[a];
+      for (int half = 0; half < 2; ++half) {
+        const int bidx = lane + 32 * half;
+        bool kill = false;
+        if (bidx > a && bidx < n && !((dead >> bidx) & 1ull)) {
+          const double s1 = S.o_st[bidx], e1 = S.o_ed[bidx];
+          double inter = __dsub_rn(fmin(e0, e1), fmax(s0, s1));
+          if (inter < 0.0) inter = 0.0;
+          const double uni = __dsub_rn(fmax(e0, e1), fmin(s0, s1));
+          const double iou = (uni == 0.0) ? 0.0 : __ddiv_rn(inter, uni);
+          kill = iou > thd;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, kill);
+        dead |= static_cast<unsigned long long>(m) << (32 * half);
+        alive -= __popc(m);
+      }
+    }
+    if (lane == 0) {  // compact in place: cnt <= a
+      S.st[cnt] = S.o_st[a]; S.ed[cnt] = S.o_ed[a]; S.sc[cnt] = S.o_sc[a]; S.src[cnt] = S.o_src[a];
+    }
+    dead |= 1ull << a;
+    --alive;
+    ++cnt;
+  }
+  __syncwarp();
+  for (int r = lane; r < cnt; r += 32) {
+    S.o_st[r] = S.st[r]; S.o_ed[r] = S.ed[r]; S.o_sc[r] = S.sc[r]; S.o_src[r] = S.src[r];
+  }
+  if (lane == 0) S.o_cnt = cnt;
+  __syncwarp();
+}
+
+__device__ void run_nms_and_store(NmsSmem& S, int n, int mode, double thd, int max_after, int M,
+                                  float* out_w, int* out_order, int* out_count, int lane) {
+  if (mode == FVTG_NMS_HULL) nms_hull_warp(S, n, thd, max_after, lane);
+  else nms_f32_warp(S, n, static_cast<float>(thd), mode, lane);
+  const int cnt = S.o_cnt;
+  for (int r = lane; r < M; r += 32) {
+    const bool v = r < cnt;
+    if (out_w) {
+      out_w[r * 3 + 0] = v ? S.o_st[r] : 0.f;
+      out_w[r * 3 + 1] = v ? S.o_ed[r] : 0.f;
+      out_w[r * 3 + 2] = v ? S.o_sc[r] : 0.f;
+    }
+    if (out_order) out_order[r] = v ? S.o_src[r] : -1;
+  }
+  if (lane == 0 && out_count) *out_count = cnt;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const int npow2,
+                  const float* __restrict__ cls, const float* __restrict__ conf,
+                  const float* __restrict__ coord, const int* __restrict__ vlen,
+                  const float* __restrict__ duration, const FvtgDecodeOut out) {
+  extern __shared__ __align__(16) uint8_t dec_smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dec_smem);
+  NmsSmem& S = *reinterpret_cast<NmsSmem*>(dec_smem + static_cast<size_t>(npow2) * 8);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int vl = vlen[b];
+  int offs[FVTG_MAX_LEVELS + 1];
+  offs[0] = 0;
+#pragma unroll
+  for (int l = 0; l < FVTG_MAX_LEVELS; ++l)
+    offs[l + 1] = offs[l] + (l < p.num_levels ? (vl >> l) : 0);
+  const int N = offs[FVTG_MAX_LEVELS] < n_max ? offs[FVTG_MAX_LEVELS] : n_max;
+  const float omx = __fsub_rn(1.f, p.x);
+  const float* cl = cls + static_cast<size_t>(b) * n_max;
+  const float* cf = conf + static_cast<size_t>(b) * n_max;
+  // ASR mix + sigmoid -> sort keys (score bits, then lower point index first)
+  for (int n = tid; n < npow2; n += DEC_THREADS) {
+    unsigned long long key = 0ull;
+    if (n < N) {
+      const float logit = __fadd_rn(__fmul_rn(p.x, cl[n]), __fmul_rn(omx, cf[n]));
+      const float score = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
+      key = (static_cast<unsigned long long>(__float_as_uint(score)) << 32) |
+            static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(n));
+    }
+    keys[n] = key;
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow2; i += DEC_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], c = keys[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int topk = p.topk;
+  const int top = N < topk ? N : topk;
+  const float dur = duration ? duration[b] : 3.0e38f;
+  if (tid < NMS_MAX) {
+    float st = 0.f, ed = 0.f, sc = 0.f;
+    if (tid < top) {
+      const unsigned long long key = keys[tid];
+      const int n = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFull));
+      sc = __uint_as_float(static_cast<unsigned>(key >> 32));
+      int l = 0;
+#pragma unroll
+      for (int i = 1; i < FVTG_MAX_LEVELS; ++i)
+        if (i < p.num_levels && n >= offs[i] && offs[i + 1] > offs[i]) l = i;
+      const float stride = static_cast<float>(1 << l);
+      const float t = static_cast<float>((n - offs[l]) << l);
+      const float d0 = coord[(static_cast<size_t>(b) * n_max + n) * 2 + 0];
+      const float d1 = coord[(static_cast<size_t>(b) * n_max + n) * 2 + 1];
+      // model.py:257-260: b[:,0] *= -1 ; b *= stride ; b += t ; b /= (1/clip_len)
+      st = __fdiv_rn(__fadd_rn(__fmul_rn(-d0, stride), t), p.inv_clip_len);
+      ed = __fdiv_rn(__fadd_rn(__fmul_rn(d1, stride), t), p.inv_clip_len);
+    }
+    if (tid < topk) {
+      if (out.boundary) {
+        float* o = out.boundary + (static_cast<size_t>(b) * topk + tid) * 3;
+        o[0] = st; o[1] = ed; o[2] = sc;
+      }
+      // inference.py:286-290: clamp all three columns to [0, duration], 4-dp
+      float w0 = round4_f32(clampf(st, 0.f, dur));
+      float w1 = round4_f32(clampf(ed, 0.f, dur));
+      float w2 = round4_f32(clampf(sc, 0.f, dur));
+      // postprocessing.py:38-50
+      if (p.clip_ts) { w0 = clampf(w0, p.min_ts, p.max_ts); w1 = clampf(w1, p.min_ts, p.max_ts); }
+      if (p.round_multiple) {
+        w0 = __fmul_rn(rintf(__fdiv_rn(w0, p.clip_len)), p.clip_len);
+        w1 = __fmul_rn(rintf(__fdiv_rn(w1, p.clip_len)), p.clip_len);
+      }
+      w2 = round4_f32(w2);
+      if (tid >= top) { w0 = w1 = w2 = 0.f; }
+      if (out.windows) {
+        float* o = out.windows + (static_cast<size_t>(b) * topk + tid) * 3;
+        o[0] = w0; o[1] = w1; o[2] = w2;
+      }
+      S.st[tid] = w0; S.ed[tid] = w1; S.sc[tid] = w2; S.src[tid] = tid;
+    }
+  }
+  if (tid == 0 && out.count) out.count[b] = top;
+  __syncthreads();
+  if (p.nms_mode != FVTG_NMS_NONE && tid < 32) {
+    run_nms_and_store(S, top, p.nms_mode, p.nms_thd, p.max_after_nms, topk,
+                      out.nms_windows ? out.nms_windows + static_cast<size_t>(b) * topk * 3 : nullptr,
+                      out.nms_order ? out.nms_order + static_cast<size_t>(b) * topk : nullptr,
+                      out.nms_count ? out.nms_count + b : nullptr, tid);
+  }
+}
+
+__global__ void __launch_bounds__(32)
+temporal_nms_kernel(const float* __restrict__ windows, const int* __restrict__ count, int M,
+                    double thd, int mode, int max_after, float* __restrict__ out_w,
+                    int* __restrict__ order, int* __restrict__ out_count) {
+  __shared__ NmsSmem S;
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int n = count ? count[b] : M;
+  if (n > M) n = M;
+  if (n < 0) n = 0;
+  for (int r = lane; r < n; r += 32) {
+    const float* w = windows + (static_cast<size_t>(b) * M + r) * 3;
+    S.st[r] = w[0]; S.ed[r] = w[1]; S.sc[r] = w[2]; S.src[r] = r;
+  }
+  __syncwarp();
+  if (n == 0) {
+    for (int r = lane; r < M; r += 32) {
+      if (out_w) { float* o = out_w + (static_cast<size_t>(b) * M + r) * 3; o[0] = o[1] = o[2] = 0.f; }
+      if (order) order[static_cast<size_t>(b) * M + r] = -1;
+    }
+    if (lane == 0 && out_count) out_count[b] = 0;
+    return;
+  }
+  run_nms_and_store(S, n, mode, thd, max_after, M,
+                    out_w ? out_w + static_cast<size_t>(b) * M * 3 : nullptr,
+                    order ? order + static_cast<size_t>(b) * M : nullptr,
+                    out_count ? out_count + b : nullptr, lane);
+}
+
+int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv, int n_max,
+                      const float* cls, const float* conf, const float* coord, const int* vlen,
+                      const float* duration, const FvtgDecodeOut& out) {
+  if (B <= 0) return FVTG_OK;
+  if (p.topk < 1 || p.topk > NMS_MAX) return fail(FVTG_EINVAL, "decode: topk must be 1..64");
+  if (n_max < 1 || n_max > 4096) return fail(FVTG_EINVAL, "decode: n_max %d out of range", n_max);
+  if (p.nms_mode < FVTG_NMS_NONE || p.nms_mode > FVTG_NMS_HULL)
+    return fail(FVTG_EINVAL, "decode: unknown nms_mode %d", p.nms_mode);
+  int npow2 = 64;
+  while (npow2 < n_max) npow2 <<= 1;
+  const size_t smem = static_cast<size_t>(npow2) * 8 + sizeof(NmsSmem);
+  ProfScope prof(st, PC_DECODE);
+  decode_nms_kernel<<<B, DEC_THREADS, smem, st>>>(p, Lv, n_max, npow2, cls, conf, coord, vlen,
+                                                   duration, out);
+  FVTG_LAUNCH_CHECK("decode_nms_kernel");
+  return FVTG_OK;
+}
+
+int launch_temporal_nms(cudaStream_t st, const float* windows, const int* count, int B, int M,
+                        double thd, int mode, int max_after, float* out_windows, int* order,
+                        int* out_count) {
+  if (B <= 0) return FVTG_OK;
+  if (M < 1 || M > NMS_MAX) return fail(FVTG_EINVAL, "temporal_nms: M must be 1..64");
+  if (mode < FVTG_NMS_NORMAL || mode > FVTG_NMS_HULL)
+    return fail(FVTG_EINVAL, "temporal_nms: unknown mode %d", mode);
+  ProfScope prof(st, PC_DECODE);
+  temporal_nms_kernel<<<B, 32, 0, st>>>(windows, count, M, thd, mode, max_after, out_windows,
+                                         order, out_count);
+  FVTG_LAUNCH_CHECK("temporal_nms_kernel");
+  return FVTG_OK;
+}
+
+}  // namespace fvtg

@@ -393,6 +393,7 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
   const int m_tiles = (args.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = m_tiles * (args.N / args.BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  ProfScope prof(st, PC_GEMM);
   gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, ta2, tb, args);
   FVTG_LAUNCH_CHECK("gemm_kernel");
   return FVTG_OK;

@@ -1,0 +1,53 @@
+// Launchers of the non-GEMM kernels of the hot path (definitions in prep.cu, attn.cu,
+// saliency.cu, decode_nms.cu).  All take device pointers + a stream, allocate nothing, never sync.
+#pragma once
+#include "common.cuh"
+
+namespace fvtg {
+
+// ---- prep.cu : HBM-bound staging ------------------------------------------------------------
+// LayerNorm over the raw feature dim (model.py:784-785) fused with the fp32 -> bf16 cast:
+// in fp32 [rows][dim] -> out bf16 [rows][dim_pad] (columns >= dim zero).
+int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const float* beta,
+                   bf16* out, int rows, int dim, int dim_pad);
+// Sine position table (position_encoding.py:61-72) for every video row of the chunk:
+// pos fp32 [B*Lv][256]; rows >= vlen[b] are zero.
+int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv);
+// Initial dummy-encoder stream: rows [b*S + j], j < nd, of X (fp32), Xb = bf16(X),
+// XPb = bf16(X + dummy_pos); and the [dummy_pos ‖ 0] position table pos_d fp32 [S][256].
+int launch_fill_dummy(cudaStream_t st, const float* dtok, const float* dpos, float* X, bf16* Xb,
+                      bf16* XPb, float* pos_d, int B, int S, int nd);
+// Pyramid level 0 (blocks.py:35, in-place ReLU): F fp32 [B*Lv][256] -> relu -> bf16 into the chain
+// buffer (pitch P0, pad rows zero) and the two head layouts H1 / H2.
+int launch_level0(cudaStream_t st, const float* F, bf16* chain0, bf16* H1, bf16* H2, int B, int Lv,
+                  const PyrGeo& geo);
+
+// ---- attn.cu : per-(video, head) attention on legacy warp MMA ----------------------------------
+struct AttnArgs {
+  const bf16* q; int ldq;   // query rows  [b*Lq + i][ldq], head h at columns h*32
+  const bf16* k; int ldk;   // key rows    [b*Lk + j][ldk]
+  const bf16* v; int ldv;   // value rows  [b*Lk + j][ldv]
+  bf16* out;                // [b*Lq + i][256]
+  int B, Lq, Lk;
+  const int* klen_src;      // per-video length added to kbase: valid keys = kbase + klen_src[b]
+  int kbase;
+  int v_first;              // keys < v_first contribute no value (the dummy tokens, crossattention.py:385-386)
+  float* tsum;              // optional fp32 [8][B*Lq]: += sum of probabilities over keys >= v_first
+};
+int launch_attention(cudaStream_t st, const AttnArgs& a);
+
+// ---- saliency.cu ---------------------------------------------------------------------------
+// saliency (transformer.py:106-113) + t2vattnvalues finalisation (model.py:215-216).
+int launch_saliency(cudaStream_t st, const float* F, const int* vlen, const float* w1,
+                    const float* b1, const float* w2t, const float* b2, const float* tsum,
+                    int t2v_layers, float* sal_out, float* t2v_out, int B, int Lv);
+
+// ---- decode_nms.cu -------------------------------------------------------------------------
+int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv, int n_max,
+                      const float* cls, const float* conf, const float* coord, const int* vlen,
+                      const float* duration, const FvtgDecodeOut& out);
+int launch_temporal_nms(cudaStream_t st, const float* windows, const int* count, int B, int M,
+                        double thd, int mode, int max_after, float* out_windows, int* order,
+                        int* out_count);
+
+}  // namespace fvtg

@@ -1,0 +1,259 @@
+"""FlashVTGB200 - drop-in for the reference's `FlashVTG` module on the inference hot path.
+
+Mirrors the reference operator interface (FlashVTG/model.py:73-304, built by `build_model1`
+model.py:792-829): same constructor source (the parsed options), same `load_state_dict` key layout,
+same `forward(src_txt, src_txt_mask, src_vid, src_vid_mask, vid, qid, targets)` keyword signature
+and the same output dict.  All arithmetic happens in libflashvtg_b200.so (hand-written sm_100a
+kernels behind the C-ABI of include/flashvtg_b200.h); this file only owns device buffers and the
+stream (PyTorch as plumbing).  There is no CPU or eager-PyTorch fallback: CPU tensors raise.
+
+Extension over the reference (which asserts bs == 1, model.py:248): batches of B videos, each
+processed with its own true lengths exactly as a bs=1 call would; `infer()` is the
+batched entry point, `forward()` keeps the reference's return shapes when B == 1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .config import ModelConfig, postprocessor_preset
+from .weights import PackedWeights, check_state_dict, expected_shapes, make_cfg_struct
+
+_NMS_MODES = {"none": _lib.NMS_NONE, None: _lib.NMS_NONE, "normal": _lib.NMS_NORMAL,
+              "linear": _lib.NMS_LINEAR, "hull": _lib.NMS_HULL}
+
+
+@dataclass
+class FvtgResult:
+    """Device tensors of one batched forward (B videos)."""
+    saliency: torch.Tensor        # (B, Lv) fp32      == outputs["saliency_scores"]
+    t2vattn: torch.Tensor         # (B, Lv) fp32      == outputs["t2vattnvalues"]
+    dummy_tokens: Optional[torch.Tensor]  # (B, nd, 256) fp32
+    video_emb: Optional[torch.Tensor]     # (B, Lv, 256) fp32, encoder output before the pyramid ReLU
+    cls_logit: Optional[torch.Tensor]     # (B, N) fp32
+    conf_logit: Optional[torch.Tensor]    # (B, N) fp32
+    coord: Optional[torch.Tensor]         # (B, N, 2) fp32  == out_coord
+    boundary: torch.Tensor        # (B, topk, 3) fp32 ranked raw (st, ed, score) == _out["boundary"]
+    windows: torch.Tensor         # (B, topk, 3) fp32 after clamp / 4-dp / PostProcessorDETR
+    nms_windows: Optional[torch.Tensor]   # (B, topk, 3) fp32 after post_processing_mr_nms
+    nms_order: Optional[torch.Tensor]     # (B, topk) int32 index into `windows`
+    count: torch.Tensor           # (B,) int32 valid rows of boundary / windows
+    nms_count: Optional[torch.Tensor]     # (B,) int32
+    launches: int                 # kernels + async copies enqueued by this call
+
+
+class FlashVTGB200(torch.nn.Module):
+    def __init__(self, cfg: ModelConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.max_num_moment = cfg.max_num_moment
+        self._sd: Optional[dict] = None
+        self._packed: dict = {}          # device -> PackedWeights
+        self._ws: dict = {}              # device -> uint8 workspace tensor
+        self._cfg_struct = make_cfg_struct(cfg)
+        self._lib = None
+
+    # ------------------------------------------------------------------ construction / weights
+    @classmethod
+    def from_opt(cls, opt) -> "FlashVTGB200":
+        """From the reference's parsed options, like build_model1(args) (model.py:792)."""
+        return cls(ModelConfig.from_opt(opt))
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):  # noqa: ARG002
+        missing, unexpected = check_state_dict(self.cfg, state_dict, strict)
+        exp = expected_shapes(self.cfg)
+        self._sd = {k: state_dict[k].detach().to("cpu", torch.float32).clone() for k in exp}
+        self._packed.clear()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def state_dict(self, *args, **kwargs):  # noqa: ARG002
+        if self._sd is None:
+            raise RuntimeError("FlashVTGB200 has no weights yet: call load_state_dict first")
+        return dict(self._sd)
+
+    def _weights(self, device: torch.device) -> PackedWeights:
+        if self._sd is None:
+            raise RuntimeError("FlashVTGB200 has no weights yet: call load_state_dict first")
+        key = (device.type, device.index)
+        if key not in self._packed:
+            self._packed[key] = PackedWeights(self.cfg, self._sd, device)
+        return self._packed[key]
+
+    def _workspace(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.type, device.index)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def decode_params(self, nms: Optional[str] = "normal", nms_thd: Optional[float] = None,
+                      max_after_nms: int = 100) -> "_lib.FvtgDecodeParams":
+        cfg = self.cfg
+        clip_ts, mn, mx, rnd = postprocessor_preset(cfg)
+        p = _lib.FvtgDecodeParams()
+        p.nms_thd = float(cfg.nms_thd if nms_thd is None else nms_thd)
+        p.x = float(self._sd["x"]) if self._sd is not None else 0.5
+        p.clip_len = cfg.clip_length
+        p.inv_clip_len = 1.0 / cfg.clip_length   # rounded once fp64 -> fp32 by ctypes, like torch
+        p.min_ts, p.max_ts = mn, mx
+        p.topk = cfg.max_num_moment
+        p.num_levels = cfg.num_levels
+        p.clip_ts, p.round_multiple = int(clip_ts), int(rnd)
+        p.nms_mode = _NMS_MODES[nms]
+        p.max_after_nms = max_after_nms
+        return p
+
+    # ------------------------------------------------------------------------------- batched API
+    @torch.no_grad()
+    def infer(self, src_vid: torch.Tensor, vid_len: torch.Tensor, src_txt: torch.Tensor,
+              txt_len: torch.Tensor, duration: Optional[torch.Tensor] = None,
+              nms: Optional[str] = "normal", nms_thd: Optional[float] = None,
+              want_heads: bool = False, want_emb: bool = False,
+              want_dummy: bool = False) -> FvtgResult:
+        """Whole hot path for B videos on the current CUDA stream (no host sync).
+
+        src_vid fp32 (B, Lv, Dv) with TEF appended, src_txt fp32 (B, Lt, Dt), vid_len / txt_len
+        int32 (B,) true lengths, duration fp32 (B,) seconds (default vid_len * clip_length)."""
+        if self._lib is None:
+            self._lib = _lib.load()
+        lib = self._lib
+        cfg = self.cfg
+        if not src_vid.is_cuda:
+            raise RuntimeError("FlashVTGB200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        dev = src_vid.device
+        for name, t, dt in (("src_vid", src_vid, torch.float32), ("src_txt", src_txt, torch.float32),
+                            ("vid_len", vid_len, torch.int32), ("txt_len", txt_len, torch.int32)):
+            if t.device != dev or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous {dt} tensor on {dev}")
+        B, Lv, Dv = src_vid.shape
+        Bt, Lt, Dt = src_txt.shape
+        if Bt != B or Dv != cfg.v_feat_dim or Dt != cfg.t_feat_dim:
+            raise ValueError(f"bad input shapes {tuple(src_vid.shape)} / {tuple(src_txt.shape)} for "
+                             f"v_feat_dim {cfg.v_feat_dim}, t_feat_dim {cfg.t_feat_dim}")
+        # generator.py:60: the reference asserts each level fits the anchor buffer
+        assert Lv <= cfg.buffer_size, "anchor buffer overflow"
+        if duration is None:
+            duration = vid_len.to(torch.float32) * cfg.clip_length
+        duration = duration.to(device=dev, dtype=torch.float32).contiguous()
+        W = self._weights(dev)
+        with torch.cuda.device(dev):
+            n_max = cfg.num_points(Lv)
+            topk = cfg.max_num_moment
+            f32 = dict(dtype=torch.float32, device=dev)
+            i32 = dict(dtype=torch.int32, device=dev)
+            sal = torch.empty(B, Lv, **f32)
+            t2v = torch.empty(B, Lv, **f32)
+            dummy = torch.empty(B, cfg.num_dummies, 256, **f32) if want_dummy else None
+            emb = torch.empty(B, Lv, 256, **f32) if want_emb else None
+            cls = torch.empty(B, n_max, **f32) if want_heads else None
+            conf = torch.empty(B, n_max, **f32) if want_heads else None
+            coord = torch.empty(B, n_max, 2, **f32) if want_heads else None
+            boundary = torch.empty(B, topk, 3, **f32)
+            windows = torch.empty(B, topk, 3, **f32)
+            count = torch.empty(B, **i32)
+            do_nms = _NMS_MODES[nms] != _lib.NMS_NONE
+            nms_w = torch.empty(B, topk, 3, **f32) if do_nms else None
+            nms_o = torch.empty(B, topk, **i32) if do_nms else None
+            nms_c = torch.empty(B, **i32) if do_nms else None
+
+            batch = _lib.FvtgBatch(B, Lv, Lt, 0, src_vid.data_ptr(), src_txt.data_ptr(),
+                                   vid_len.data_ptr(), txt_len.data_ptr())
+            fout = _lib.FvtgFusionOut(_lib.ptr(emb), sal.data_ptr(), t2v.data_ptr(), _lib.ptr(dummy))
+            hout = _lib.FvtgHeadsOut(n_max, 0, _lib.ptr(cls), _lib.ptr(conf), _lib.ptr(coord))
+            dout = _lib.FvtgDecodeOut(boundary.data_ptr(), windows.data_ptr(), _lib.ptr(nms_w),
+                                      _lib.ptr(nms_o), count.data_ptr(), _lib.ptr(nms_c))
+            dp = self.decode_params(nms, nms_thd)
+            need = lib.fvtg_workspace_bytes(C.byref(self._cfg_struct), B, Lv, Lt)
+            if need == 0:
+                raise RuntimeError("fvtg_workspace_bytes rejected the configuration: "
+                                   + lib.fvtg_last_error().decode(errors="replace"))
+            ws = self._workspace(dev, need)
+            rc = lib.fvtg_forward(C.byref(self._cfg_struct), W.ref(), C.byref(batch),
+                                  duration.data_ptr(), C.byref(dp), C.byref(fout), C.byref(hout),
+                                  C.byref(dout), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "fvtg_forward")
+            launches = int(lib.fvtg_last_launch_count())
+        return FvtgResult(sal, t2v, dummy, emb, cls, conf, coord, boundary, windows, nms_w, nms_o,
+                          count, nms_c, launches)
+
+    @torch.no_grad()
+    def decode(self, cls_logit: torch.Tensor, conf_logit: torch.Tensor, coord: torch.Tensor,
+               vid_len: torch.Tensor, Lv: int, duration: Optional[torch.Tensor] = None,
+               nms: Optional[str] = "normal", nms_thd: Optional[float] = None):
+        """Kernel group C alone (fvtg_decode_nms) on caller-supplied head outputs: ASR mix, sigmoid,
+        span decode, top-k, compose / PostProcessorDETR, NMS.  Returns (boundary, windows,
+        nms_windows, nms_order, count, nms_count)."""
+        lib = self._lib = self._lib or _lib.load()
+        cfg = self.cfg
+        dev = cls_logit.device
+        if not cls_logit.is_cuda:
+            raise RuntimeError("FlashVTGB200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        B, n_max = cls_logit.shape
+        topk = cfg.max_num_moment
+        if duration is None:
+            duration = vid_len.to(torch.float32) * cfg.clip_length
+        duration = duration.to(device=dev, dtype=torch.float32).contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        boundary = torch.empty(B, topk, 3, **f32)
+        windows = torch.empty(B, topk, 3, **f32)
+        nms_w = torch.empty(B, topk, 3, **f32)
+        nms_o = torch.empty(B, topk, **i32)
+        count = torch.empty(B, **i32)
+        nms_c = torch.empty(B, **i32)
+        dout = _lib.FvtgDecodeOut(boundary.data_ptr(), windows.data_ptr(), nms_w.data_ptr(),
+                                  nms_o.data_ptr(), count.data_ptr(), nms_c.data_ptr())
+        dp = self.decode_params(nms, nms_thd)
+        with torch.cuda.device(dev):
+            rc = lib.fvtg_decode_nms(C.byref(dp), B, Lv, n_max, cls_logit.contiguous().data_ptr(),
+                                     conf_logit.contiguous().data_ptr(), coord.contiguous().data_ptr(),
+                                     vid_len.contiguous().data_ptr(), duration.data_ptr(),
+                                     C.byref(dout), _lib.stream_ptr())
+        _lib.check(rc, "fvtg_decode_nms")
+        return boundary, windows, nms_w, nms_o, count, nms_c
+
+    # ------------------------------------------------------------------ reference forward() API
+    @torch.no_grad()
+    def forward(self, src_txt, src_txt_mask, src_vid, src_vid_mask, vid=None, qid=None,  # noqa: ARG002
+                targets=None):
+        """Same keyword signature and output dict as FlashVTG.forward in eval mode
+        (model.py:138,213-216,251-266,298-304).  `targets` must be a dict (targets.get, :251)."""
+        if self.training:
+            raise RuntimeError("FlashVTGB200 implements the inference path only: call .eval()")
+        if targets is None:
+            targets = {}
+        vid_len = src_vid_mask.sum(1).to(torch.int32)
+        txt_len = src_txt_mask.sum(1).to(torch.int32)
+        r = self.infer(src_vid.contiguous().float(), vid_len, src_txt.contiguous().float(), txt_len,
+                       nms=None, want_dummy=True)
+        B = src_vid.shape[0]
+        out = dict(_avg_factor=B)
+        out["saliency_scores"] = r.saliency
+        out["t2vattnvalues"] = r.t2vattn
+        o = dict(label=targets.get("label", [None])[0])
+        o["video_msk"] = src_vid_mask.int()
+        o["saliency"] = r.saliency[0]
+        if B == 1:
+            # reference shape (min(N, 50), 3); N depends on the true length -> one scalar D2H
+            n = int(r.count[0].item())
+            o["boundary"] = r.boundary[0, :n]
+        else:
+            o["boundary"] = r.boundary
+            o["boundary_count"] = r.count
+        out["_out"] = o
+        out["saliency_scores_neg"] = None
+        out["t2vattnvalues_neg"] = None
+        out["real_neg_mask"] = None
+        out["dummy_tokens"] = r.dummy_tokens
+        return out
+
+
+def build_model_b200(opt_or_cfg) -> FlashVTGB200:
+    """Counterpart of build_model1 (model.py:792) for the inference path (no criterion)."""
+    cfg = opt_or_cfg if isinstance(opt_or_cfg, ModelConfig) else ModelConfig.from_opt(opt_or_cfg)
+    return FlashVTGB200(cfg).eval()

@@ -1,0 +1,139 @@
+"""Host mirror of the reference's list-based post-processing API, backed by the CUDA kernels.
+
+  temporal_nms            : batched device entry (fvtg_temporal_nms)
+  post_processing_mr_nms  : same signature / in-place semantics as FlashVTG/inference.py:36-57
+  temporal_nms_list       : same signature as utils/temporal_nms.py:25 (the hull variant)
+  compute_mr_results      : counterpart of FlashVTG/inference.py:232-355 for a FlashVTGB200 model -
+                            forward + compose (clamp, 4-dp) + PostProcessorDETR in one device pass
+
+No CPU fallback: everything below needs the sm_100a library and a CUDA device.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_MODES = {"normal": _lib.NMS_NORMAL, "linear": _lib.NMS_LINEAR, "hull": _lib.NMS_HULL}
+
+
+def temporal_nms(windows: torch.Tensor, count: Optional[torch.Tensor], thd: float,
+                 mode: str = "normal", max_after_nms: int = 100):
+    """windows fp32 (B, M, 3) CUDA rows (st, ed, score), count int32 (B,) or None (= M each).
+    Returns (out_windows (B,M,3), order (B,M) int32 source row or -1, out_count (B,) int32)."""
+    if mode not in _MODES:
+        raise ValueError(f"Unknown nms_type: {mode}")  # inference.py:50
+    if not windows.is_cuda:
+        raise RuntimeError("temporal_nms runs on a CUDA (sm_100a) device only; there is no CPU path")
+    if windows.dtype != torch.float32 or windows.dim() != 3 or windows.shape[2] != 3:
+        raise ValueError("windows must be fp32 (B, M, 3)")
+    windows = windows.contiguous()
+    B, M, _ = windows.shape
+    lib = _lib.load()
+    out = torch.empty_like(windows)
+    order = torch.empty(B, M, dtype=torch.int32, device=windows.device)
+    ocount = torch.empty(B, dtype=torch.int32, device=windows.device)
+    if B == 0:
+        return out, order, ocount
+    if count is not None:
+        count = count.to(device=windows.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(windows.device):
+        rc = lib.fvtg_temporal_nms(windows.data_ptr(), _lib.ptr(count), B, M, float(thd), _MODES[mode],
+                                   int(max_after_nms), out.data_ptr(), order.data_ptr(),
+                                   ocount.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "fvtg_temporal_nms")
+    return out, order, ocount
+
+
+def _batch_lists(lists, device):
+    n = [len(w) for w in lists]
+    M = max(max(n), 1) if n else 1
+    if M > _lib.MAX_TOPK:
+        raise ValueError(f"at most {_lib.MAX_TOPK} windows per query are supported (got {M}); the "
+                         "reference never produces more than max_num_moment = 50")
+    buf = np.zeros((len(lists), M, 3), np.float32)
+    for i, w in enumerate(lists):
+        if n[i]:
+            buf[i, : n[i]] = np.asarray(w, dtype=np.float64).astype(np.float32).reshape(-1, 3)
+    return (torch.from_numpy(buf).to(device, non_blocking=False),
+            torch.tensor(n, dtype=torch.int32, device=device), n)
+
+
+def post_processing_mr_nms(mr_res, nms_thd, max_before_nms, max_after_nms, nms_type,  # noqa: ARG001
+                           device="cuda"):
+    """Drop-in for FlashVTG/inference.py:36-57: every entry's "pred_relevant_windows" is replaced
+    by the NMS result (all rows kept, suppressed scores zeroed, sorted by score descending).
+    `max_before_nms` / `max_after_nms` are accepted and ignored, exactly like the reference."""
+    if nms_type not in ("normal", "linear"):
+        raise ValueError(f"Unknown nms_type: {nms_type}")
+    if not mr_res:
+        return []
+    win, cnt, n = _batch_lists([e["pred_relevant_windows"] for e in mr_res], torch.device(device))
+    out, _, _ = temporal_nms(win, cnt, nms_thd, nms_type)
+    out = out.cpu()
+    res = []
+    for i, e in enumerate(mr_res):
+        e["pred_relevant_windows"] = out[i, : n[i]].tolist()
+        res.append(e)
+    return res
+
+
+def temporal_nms_list(predictions, nms_thd, max_after_nms=100, device="cuda"):
+    """Drop-in for utils/temporal_nms.py:25-74 (hull 'union', strict >, removal) on one list.
+    Rows come back as the original python floats (the reference only re-orders / drops them)."""
+    if len(predictions) == 1:
+        return predictions
+    if not predictions:
+        return []
+    win64 = [list(map(float, p)) for p in predictions]
+    if len(win64) > _lib.MAX_TOPK:
+        raise ValueError(f"at most {_lib.MAX_TOPK} windows are supported")
+    # the kernel compares in fp64 on the fp32 inputs it is given; exactness needs fp32-exact rows
+    w32 = np.asarray(win64, np.float64).astype(np.float32)
+    if not np.array_equal(w32.astype(np.float64), np.asarray(win64, np.float64)):
+        raise ValueError("temporal_nms_list needs fp32-representable windows (the device entry "
+                         "takes fp32 rows); pass tensors produced by the model")
+    win = torch.from_numpy(w32[None]).to(device)
+    _, order, cnt = temporal_nms(win, None, nms_thd, "hull", max_after_nms)
+    k = int(cnt[0].item())
+    return [predictions[j] for j in order[0, :k].tolist()]
+
+
+def round4_host(x: np.ndarray) -> np.ndarray:
+    """float(f"{e:.4f}") vectorised: fp32 -> fp64, x*1e4 exact, rint half-even, /1e4."""
+    return np.rint(np.asarray(x, np.float64) * 1e4) / 1e4
+
+
+@torch.no_grad()
+def compute_mr_results(model, eval_loader, opt=None, nms: Optional[str] = None):
+    """Counterpart of compute_mr_results (inference.py:232-355) for a FlashVTGB200 model.
+
+    eval_loader yields the reference's (query_meta, batched_inputs) pairs where batched_inputs is
+    the dict `prepare_batch_inputs` returns (src_txt, src_txt_mask, src_vid, src_vid_mask); any
+    batch size is accepted.  Returns the same list of dicts (qid, query, vid,
+    pred_relevant_windows, pred_saliency_scores) AFTER PostProcessorDETR; with `nms` set the
+    windows additionally went through post_processing_mr_nms on the device."""
+    mr_res = []
+    for query_meta, inp in eval_loader:
+        dev = inp["src_vid"].device
+        vid_len = inp["src_vid_mask"].sum(1).to(torch.int32)
+        txt_len = inp["src_txt_mask"].sum(1).to(torch.int32)
+        dur = torch.tensor([float(m["duration"]) for m in query_meta], dtype=torch.float32, device=dev)
+        r = model.infer(inp["src_vid"].contiguous().float(), vid_len,
+                        inp["src_txt"].contiguous().float(), txt_len, duration=dur, nms=nms,
+                        nms_thd=getattr(opt, "nms_thd", None))
+        win = (r.nms_windows if nms else r.windows).cpu().numpy()
+        cnt = r.count.cpu().tolist()
+        sal = r.saliency.cpu().numpy()
+        vl = vid_len.cpu().tolist()
+        for i, meta in enumerate(query_meta):
+            w = win[i, : cnt[i]].astype(np.float64)
+            if not nms:
+                w[:, 2] = round4_host(w[:, 2])   # the 4-dp score is a python float (postprocessing.py:33)
+            mr_res.append(dict(qid=meta["qid"], query=meta["query"], vid=meta["vid"],
+                               pred_relevant_windows=w.tolist(),
+                               pred_saliency_scores=round4_host(sal[i, : vl[i]]).tolist()))
+    return mr_res

@@ -165,15 +165,16 @@ typedef struct FvtgHeadsOut {
 #define FVTG_NMS_HULL 2    /* utils/temporal_nms.py: hull "union", strict >, removal */
 
 typedef struct FvtgDecodeParams {
+  double nms_thd;     /* compared as fp32 in normal / linear mode (torch), as fp64 in hull mode (python) */
   float x;            /* ASR mix weight */
-  float clip_len;
+  float clip_len;     /* (float)clip_length */
+  float inv_clip_len; /* (float)(1.0 / clip_length), the divisor of model.py:260, rounded once from fp64 */
+  float min_ts, max_ts;
   int32_t topk;       /* max_num_moment */
   int32_t num_levels;
   int32_t clip_ts;    /* 1: apply clip_min_max_timestamps (postprocessing.py:38-43) */
-  float min_ts, max_ts;
   int32_t round_multiple; /* 1: round_to_multiple_clip_lengths (postprocessing.py:45-50) */
   int32_t nms_mode;   /* FVTG_NMS_* */
-  float nms_thd;
   int32_t max_after_nms; /* hull mode only */
   int32_t _pad;
 } FvtgDecodeParams;
@@ -208,7 +209,7 @@ int32_t fvtg_decode_nms(const FvtgDecodeParams* p, int32_t B, int32_t Lv, int32_
  * Outputs: out_windows [B][M][3] in final order, order [B][M] (index of the source row),
  * out_count [B].  Bit-exact with the reference arithmetic (fp32 for normal/linear, fp64 for hull). */
 int32_t fvtg_temporal_nms(const float* windows, const int32_t* count, int32_t B, int32_t M,
-                          float thd, int32_t mode, int32_t max_after_nms, float* out_windows,
+                          double thd, int32_t mode, int32_t max_after_nms, float* out_windows,
                           int32_t* order, int32_t* out_count, void* stream);
 
 /* Whole path (fusion -> pyramid+heads -> decode/NMS), chunk by chunk so each chunk's intermediates
@@ -222,6 +223,14 @@ int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* 
 int64_t fvtg_last_launch_count(void);
 const char* fvtg_last_error(void);
 int32_t fvtg_abi_version(void);
+
+/* Bench hook.  fvtg_prof_enable(1): every kernel launched by this thread's later fvtg_* calls is
+ * bracketed by a CUDA event pair on its stream.  fvtg_prof_collect waits for them and returns, per
+ * kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm+cast staging, 3 decode/NMS, 4 other),
+ * the summed device time in ms and the launch count since the last collect. */
+#define FVTG_PROF_CLASSES 5
+void fvtg_prof_enable(int32_t on);
+int32_t fvtg_prof_collect(double* ms, int64_t* launches, int32_t n_classes);
 
 /* Test hook: out = act(A[M][K] * W[N][K]^T + bias) through the production tcgen05 GEMM.
  * A, W bf16 (K multiple of 64, N multiple of 128).  N == 256: out is fp32 [M][256] (full-row
