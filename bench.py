@@ -229,6 +229,15 @@ def run_ours(args):
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
 
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                              "steps": args.steps, "ms_per_step": ms / args.steps,
+                              "gpu_launches": int(launches_per_step * args.steps),
+                              "note": "kernel-only run (profiling aid), not a bench line"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     # ---- e2e: same metric through the public API with HOST buffers (H2D + D2H inside) ----------
     out_host = {k: torch.empty(s, dtype=dt).pin_memory() for k, s, dt in (
         ("nms_windows", (B, cfg.max_num_moment, 3), torch.float32),
@@ -325,6 +334,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="device-resident timing only (for runs under ncu): no e2e / roofline / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

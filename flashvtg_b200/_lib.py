@@ -111,6 +111,7 @@ SIGNATURES = {
     "fvtg_decode_nms": (i32, [C.POINTER(FvtgDecodeParams), i32, i32, i32, vp, vp, vp, vp, vp,
                               C.POINTER(FvtgDecodeOut), vp]),
     "fvtg_temporal_nms": (i32, [vp, vp, i32, i32, C.c_double, i32, i32, vp, vp, vp, vp]),
+    "fvtg_temporal_nms_hull_f64": (i32, [vp, vp, i32, i32, C.c_double, i32, vp, vp, vp]),
     "fvtg_forward": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgWeights), C.POINTER(FvtgBatch), vp,
                            C.POINTER(FvtgDecodeParams), C.POINTER(FvtgFusionOut),
                            C.POINTER(FvtgHeadsOut), C.POINTER(FvtgDecodeOut), vp, C.c_size_t, vp]),

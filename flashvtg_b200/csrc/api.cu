@@ -1,6 +1,6 @@
 // C-ABI entry points: validate, carve the caller's workspace, and enqueue the kernel sequence of
-// the hot path on the caller's stream, chunk by chunk (a chunk = the videos whose activations fit
-// the 126 MB L2, so only the raw features and the few-KB results touch HBM).
+// the hot path on the caller's stream, chunk by chunk (a chunk = as many videos as the workspace
+// budget allows, see chunk_videos).
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -109,15 +109,16 @@ static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws*
 static int chunk_videos(const FvtgCfg& c, int Lv, int Lt) {
   const int forced = env_int("FVTG_CHUNK", 0);
   if (forced > 0) return forced;
-  // One wave of 128-row tiles over the SMs for the N=256 GEMMs (the most frequent shape), and at
-  // most ~96 MB of per-chunk activations so the chunk stays L2 resident.
-  int sms = 148;
-  int bc = (sms * GEMM_BM) / (Lv > 0 ? Lv : 1);
-  if (bc < 1) bc = 1;
+  // Large chunks: every kernel of the sequence is latency / epilogue bound below a few waves of
+  // 128-row tiles (measured: 34 k videos/s at 78-video chunks vs 99 k at 1024, profiles/r01_*),
+  // so a chunk is capped only by row count and workspace size, not by L2 residency.
   const size_t per_video = carve(c, 1, Lv, Lt, nullptr, nullptr);
-  const size_t budget = static_cast<size_t>(env_int("FVTG_L2_MB", 160)) << 20;
-  while (bc > 1 && per_video * bc > budget) bc = (bc * 3) / 4;
-  return bc;
+  const size_t budget = static_cast<size_t>(env_int("FVTG_WS_MB", 4096)) << 20;
+  long long bc = 131072 / (Lv > 0 ? Lv : 1);
+  if (bc < 1) bc = 1;
+  if (static_cast<size_t>(bc) * per_video > budget) bc = static_cast<long long>(budget / per_video);
+  if (bc < 1) bc = 1;
+  return static_cast<int>(bc);
 }
 
 static int check_cfg(const FvtgCfg* c) {
@@ -552,6 +553,16 @@ int32_t fvtg_temporal_nms(const float* windows, const int32_t* count, int32_t B,
   FVTG_TRY(check_arch());
   return launch_temporal_nms(static_cast<cudaStream_t>(stream), windows, count, B, M, thd, mode,
                              max_after_nms, out_windows, order, out_count);
+}
+
+int32_t fvtg_temporal_nms_hull_f64(const double* windows, const int32_t* count, int32_t B, int32_t M,
+                                   double thd, int32_t max_after_nms, int32_t* order,
+                                   int32_t* out_count, void* stream) {
+  host_state().launches = 0;
+  if (!windows || !order) return fail(FVTG_EINVAL, "temporal_nms_hull_f64: null argument");
+  FVTG_TRY(check_arch());
+  return launch_temporal_nms_hull_f64(static_cast<cudaStream_t>(stream), windows, count, B, M, thd,
+                                      max_after_nms, order, out_count);
 }
 
 int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* in,

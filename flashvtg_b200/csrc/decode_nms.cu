@@ -109,25 +109,30 @@ __device__ void nms_f32_warp(NmsSmem& S, int n, float thd, int mode, int lane) {
   __syncwarp();
 }
 
-// utils/temporal_nms.py on n <= 64 rows, fp64 arithmetic, one full warp.
-__device__ void nms_hull_warp(NmsSmem& S, int n, double thd, int max_after, int lane) {
-  if (n == 1) {
-    if (lane == 0) {
-      S.o_st[0] = S.st[0]; S.o_ed[0] = S.ed[0]; S.o_sc[0] = S.sc[0]; S.o_src[0] = S.src[0];
-      S.o_cnt = 1;
-    }
+// utils/temporal_nms.py on n <= 64 rows, fp64 arithmetic (python floats), one full warp.
+// Input rows in H.st / H.ed / H.sc; result: H.out[0..H.cnt) = source rows kept, in output order.
+struct HullSmem {
+  double st[NMS_MAX], ed[NMS_MAX], sc[NMS_MAX];
+  int idx[NMS_MAX];   // rows in stable descending score order
+  int out[NMS_MAX];
+  int cnt;
+};
+
+__device__ void nms_hull_warp(HullSmem& H, int n, double thd, int max_after, int lane) {
+  if (n == 1) {  // temporal_nms.py:37-38: a single prediction is returned as is
+    if (lane == 0) { H.out[0] = 0; H.cnt = 1; }
     __syncwarp();
     return;
   }
-  // stable descending sort by score into o_* (python sorted(reverse=True) keeps input order on ties)
+  // stable descending sort by score (python sorted(reverse=True) keeps input order on ties)
   for (int r = lane; r < n; r += 32) {
-    const float s = S.sc[r];
+    const double s = H.sc[r];
     int rank = 0;
     for (int q = 0; q < n; ++q) {
-      const float sq = S.sc[q];
+      const double sq = H.sc[q];
       if (q != r && (sq > s || (sq == s && q < r))) ++rank;
     }
-    S.o_st[rank] = S.st[r]; S.o_ed[rank] = S.ed[r]; S.o_sc[rank] = s; S.o_src[rank] = S.src[r];
+    H.idx[rank] = r;
   }
   __syncwarp();
   unsigned long long dead = 0ull;
@@ -136,12 +141,12 @@ __device__ void nms_hull_warp(NmsSmem& S, int n, double thd, int max_after, int 
     if ((dead >> a) & 1ull) continue;
     if (cnt >= max_after) break;
     if (alive > 1) {
-      const double s0 = S.o_st[a], e0 = S.o_ed[a];
+      const double s0 = H.st[H.idx[a]], e0 = H.ed[H.idx[a]];
       for (int half = 0; half < 2; ++half) {
         const int bidx = lane + 32 * half;
         bool kill = false;
         if (bidx > a && bidx < n && !((dead >> bidx) & 1ull)) {
-          const double s1 = S.o_st[bidx], e1 = S.o_ed[bidx];
+          const double s1 = H.st[H.idx[bidx]], e1 = H.ed[H.idx[bidx]];
           double inter = __dsub_rn(fmin(e0, e1), fmax(s0, s1));
           if (inter < 0.0) inter = 0.0;
           const double uni = __dsub_rn(fmax(e0, e1), fmin(s0, s1));
@@ -153,25 +158,31 @@ __device__ void nms_hull_warp(NmsSmem& S, int n, double thd, int max_after, int 
         alive -= __popc(m);
       }
     }
-    if (lane == 0) {  // compact in place: cnt <= a
-      S.st[cnt] = S.o_st[a]; S.ed[cnt] = S.o_ed[a]; S.sc[cnt] = S.o_sc[a]; S.src[cnt] = S.o_src[a];
-    }
+    if (lane == 0) H.out[cnt] = H.idx[a];
     dead |= 1ull << a;
     --alive;
     ++cnt;
   }
-  __syncwarp();
-  for (int r = lane; r < cnt; r += 32) {
-    S.o_st[r] = S.st[r]; S.o_ed[r] = S.ed[r]; S.o_sc[r] = S.sc[r]; S.o_src[r] = S.src[r];
-  }
-  if (lane == 0) S.o_cnt = cnt;
+  if (lane == 0) H.cnt = cnt;
   __syncwarp();
 }
 
-__device__ void run_nms_and_store(NmsSmem& S, int n, int mode, double thd, int max_after, int M,
-                                  float* out_w, int* out_order, int* out_count, int lane) {
-  if (mode == FVTG_NMS_HULL) nms_hull_warp(S, n, thd, max_after, lane);
-  else nms_f32_warp(S, n, static_cast<float>(thd), mode, lane);
+__device__ void run_nms_and_store(NmsSmem& S, HullSmem& H, int n, int mode, double thd,
+                                  int max_after, int M, float* out_w, int* out_order,
+                                  int* out_count, int lane) {
+  if (mode == FVTG_NMS_HULL) {
+    for (int r = lane; r < n; r += 32) { H.st[r] = S.st[r]; H.ed[r] = S.ed[r]; H.sc[r] = S.sc[r]; }
+    __syncwarp();
+    nms_hull_warp(H, n, thd, max_after, lane);
+    for (int r = lane; r < H.cnt; r += 32) {
+      const int j = H.out[r];
+      S.o_st[r] = S.st[j]; S.o_ed[r] = S.ed[j]; S.o_sc[r] = S.sc[j]; S.o_src[r] = S.src[j];
+    }
+    if (lane == 0) S.o_cnt = H.cnt;
+    __syncwarp();
+  } else {
+    nms_f32_warp(S, n, static_cast<float>(thd), mode, lane);
+  }
   const int cnt = S.o_cnt;
   for (int r = lane; r < M; r += 32) {
     const bool v = r < cnt;
@@ -185,6 +196,8 @@ __device__ void run_nms_and_store(NmsSmem& S, int n, int mode, double thd, int m
   if (lane == 0 && out_count) *out_count = cnt;
 }
 
+constexpr size_t DEC_NMS_BYTES = (sizeof(NmsSmem) + 15) / 16 * 16;
+
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const int npow2,
                   const float* __restrict__ cls, const float* __restrict__ conf,
@@ -193,6 +206,7 @@ decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const
   extern __shared__ __align__(16) uint8_t dec_smem[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(dec_smem);
   NmsSmem& S = *reinterpret_cast<NmsSmem*>(dec_smem + static_cast<size_t>(npow2) * 8);
+  HullSmem& H = *reinterpret_cast<HullSmem*>(dec_smem + static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES);
   const int b = blockIdx.x, tid = threadIdx.x;
   const int vl = vlen[b];
   int offs[FVTG_MAX_LEVELS + 1];
@@ -278,7 +292,7 @@ decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const
   if (tid == 0 && out.count) out.count[b] = top;
   __syncthreads();
   if (p.nms_mode != FVTG_NMS_NONE && tid < 32) {
-    run_nms_and_store(S, top, p.nms_mode, p.nms_thd, p.max_after_nms, topk,
+    run_nms_and_store(S, H, top, p.nms_mode, p.nms_thd, p.max_after_nms, topk,
                       out.nms_windows ? out.nms_windows + static_cast<size_t>(b) * topk * 3 : nullptr,
                       out.nms_order ? out.nms_order + static_cast<size_t>(b) * topk : nullptr,
                       out.nms_count ? out.nms_count + b : nullptr, tid);
@@ -290,6 +304,7 @@ temporal_nms_kernel(const float* __restrict__ windows, const int* __restrict__ c
                     double thd, int mode, int max_after, float* __restrict__ out_w,
                     int* __restrict__ order, int* __restrict__ out_count) {
   __shared__ NmsSmem S;
+  __shared__ HullSmem H;
   const int b = blockIdx.x, lane = threadIdx.x;
   int n = count ? count[b] : M;
   if (n > M) n = M;
@@ -307,10 +322,42 @@ temporal_nms_kernel(const float* __restrict__ windows, const int* __restrict__ c
     if (lane == 0 && out_count) out_count[b] = 0;
     return;
   }
-  run_nms_and_store(S, n, mode, thd, max_after, M,
+  run_nms_and_store(S, H, n, mode, thd, max_after, M,
                     out_w ? out_w + static_cast<size_t>(b) * M * 3 : nullptr,
                     order ? order + static_cast<size_t>(b) * M : nullptr,
                     out_count ? out_count + b : nullptr, lane);
+}
+
+// utils/temporal_nms.py on caller fp64 rows (python floats): order / count only.
+__global__ void __launch_bounds__(32)
+temporal_nms_hull_f64_kernel(const double* __restrict__ windows, const int* __restrict__ count,
+                             int M, double thd, int max_after, int* __restrict__ order,
+                             int* __restrict__ out_count) {
+  __shared__ HullSmem H;
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int n = count ? count[b] : M;
+  if (n > M) n = M;
+  if (n < 0) n = 0;
+  for (int r = lane; r < n; r += 32) {
+    const double* w = windows + (static_cast<size_t>(b) * M + r) * 3;
+    H.st[r] = w[0]; H.ed[r] = w[1]; H.sc[r] = w[2];
+  }
+  if (lane == 0) H.cnt = 0;
+  __syncwarp();
+  if (n > 0) nms_hull_warp(H, n, thd, max_after, lane);
+  const int cnt = H.cnt;
+  for (int r = lane; r < M; r += 32) order[static_cast<size_t>(b) * M + r] = r < cnt ? H.out[r] : -1;
+  if (lane == 0 && out_count) out_count[b] = cnt;
+}
+
+int launch_temporal_nms_hull_f64(cudaStream_t st, const double* windows, const int* count, int B,
+                                 int M, double thd, int max_after, int* order, int* out_count) {
+  if (B <= 0) return FVTG_OK;
+  if (M < 1 || M > NMS_MAX) return fail(FVTG_EINVAL, "temporal_nms: M must be 1..64");
+  ProfScope prof(st, PC_DECODE);
+  temporal_nms_hull_f64_kernel<<<B, 32, 0, st>>>(windows, count, M, thd, max_after, order, out_count);
+  FVTG_LAUNCH_CHECK("temporal_nms_hull_f64_kernel");
+  return FVTG_OK;
 }
 
 int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv, int n_max,
@@ -323,7 +370,7 @@ int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv,
     return fail(FVTG_EINVAL, "decode: unknown nms_mode %d", p.nms_mode);
   int npow2 = 64;
   while (npow2 < n_max) npow2 <<= 1;
-  const size_t smem = static_cast<size_t>(npow2) * 8 + sizeof(NmsSmem);
+  const size_t smem = static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES + sizeof(HullSmem);
   ProfScope prof(st, PC_DECODE);
   decode_nms_kernel<<<B, DEC_THREADS, smem, st>>>(p, Lv, n_max, npow2, cls, conf, coord, vlen,
                                                    duration, out);

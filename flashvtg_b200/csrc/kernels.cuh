@@ -50,4 +50,7 @@ int launch_temporal_nms(cudaStream_t st, const float* windows, const int* count,
                         double thd, int mode, int max_after, float* out_windows, int* order,
                         int* out_count);
 
+int launch_temporal_nms_hull_f64(cudaStream_t st, const double* windows, const int* count, int B,
+                                 int M, double thd, int max_after, int* order, int* out_count);
+
 }  // namespace fvtg

