@@ -18,7 +18,7 @@ MAX_LEVELS = 8
 MAX_CONVS = 4
 MAX_MLP = 8
 MAX_TOPK = 64
-PROF_CLASSES = ("gemm", "attention", "ln_cast", "decode_nms", "other")
+PROF_CLASSES = ("gemm", "attention", "ln_cast", "decode_nms", "other", "layer")
 
 NMS_NONE, NMS_NORMAL, NMS_LINEAR, NMS_HULL = -1, 0, 1, 2
 

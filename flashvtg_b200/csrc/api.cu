@@ -73,14 +73,14 @@ static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws*
   t.vid_b = k.take<bf16>(Rv * c.v_dim_pad);
   t.txt_b = k.take<bf16>(Rt * c.t_dim_pad);
   t.tmp256 = k.take<bf16>(Rmax * 256);
-  t.Xf = k.take<float>(Rs * 256);
+  t.Xf = k.take<float>(round_up_sz(Rs, 128) * 256);   // tile-blocked
   t.Xb = k.take<bf16>(Rs * 256);
   t.XPb = k.take<bf16>(Rs * 256);
   t.Kc = k.take<bf16>(Rs * 256);
-  t.Yf = k.take<float>(Rv * 256);
+  t.Yf = k.take<float>(round_up_sz(Rv, 128) * 256);   // tile-blocked
   t.Yb = k.take<bf16>(Rv * 256);
   t.YPb = k.take<bf16>(Rv * 256);
-  t.pos_v = k.take<float>(Rv * 256);
+  t.pos_v = k.take<float>(round_up_sz(Rv, 128) * 256);  // tile-blocked
   t.pos_d = k.take<float>(S * 256);
   t.qkv = k.take<bf16>(Rmax * 768);
   t.att = k.take<bf16>(Rmax * 256);
@@ -141,10 +141,27 @@ static int check_cfg(const FvtgCfg* c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One post-norm self-attention layer (transformer.py:408-421) over `rows` = B * L stream rows.
+static LayerArgs layer_args(const FvtgEncLayer& L, int rows, int mode, float* yf) {
+  LayerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = rows;
+  a.mode = mode;
+  a.prelu = L.prelu;
+  a.bo = L.out_proj.b;
+  a.g1 = L.norm1.g; a.be1 = L.norm1.b;
+  a.b1 = L.ff1.b;
+  a.b2 = L.ff2.b;
+  a.g2 = L.norm2.g; a.be2 = L.norm2.b;
+  a.yf = yf;
+  return a;
+}
+
+// One post-norm self-attention layer (transformer.py:408-421) over `rows` = B * L stream rows:
+// QKV projection GEMM -> per-(video, head) attention -> fused out_proj/LN1/FFN/LN2 kernel.
+// out_b / out_pb: bf16(x) and bf16(x + pos) for the next layer's V and Q/K projections.
 static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, int Lseq, float* xf,
-                    bf16* xb, bf16* xpb, const float* pos, int pos_mod, const int* klen_src,
-                    int kbase, bf16* pos_extra, int pos_extra_rowlim) {
+                    const bf16* xb, const bf16* xpb, bf16* out_b, bf16* out_pb, const float* pos,
+                    int pos_mod, int pos_rowlim, const int* klen_src, int kbase) {
   const int rows = B * Lseq;
   {  // Q,K from x+pos ; V from x  (in_proj rows 0:512 / 512:768)
     GemmArgs g = gemm_args(rows, 768, 256, 256);
@@ -166,46 +183,20 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
     a.klen_src = klen_src; a.kbase = kbase; a.v_first = 0; a.tsum = nullptr;
     FVTG_TRY(launch_attention(st, a));
   }
-  {  // x1 = LN1(x + att Wo^T + bo)
-    GemmArgs g = gemm_args(rows, 256, 256, 256);
-    g.epi.mode = EPI_ROW;
-    g.epi.bias = L.out_proj.b;
-    g.epi.res = xf;
-    g.epi.gamma = L.norm1.g; g.epi.beta = L.norm1.b;
-    g.epi.out_f32 = xf;
-    g.epi.out_bf16 = xb;
-    FVTG_TRY(launch_gemm(st, w.att, nullptr, rows, 256, 256, L.out_proj.w, g));
-  }
-  {  // h = PReLU(x1 W1^T + b1)
-    GemmArgs g = gemm_args(rows, 1024, 256, 256);
-    g.epi.mode = EPI_TILE;
-    g.epi.bias = L.ff1.b;
-    g.epi.act = ACT_PRELU; g.epi.prelu = L.prelu;
-    g.epi.out = w.ffh; g.epi.ld_out = 1024;
-    FVTG_TRY(launch_gemm(st, xb, nullptr, rows, 256, 256, L.ff1.w, g));
-  }
-  {  // x = LN2(x1 + h W2^T + b2) ; also bf16(x + pos) for the next layer's q/k
-    GemmArgs g = gemm_args(rows, 256, 256, 1024);
-    g.epi.mode = EPI_ROW;
-    g.epi.bias = L.ff2.b;
-    g.epi.res = xf;
-    g.epi.gamma = L.norm2.g; g.epi.beta = L.norm2.b;
-    g.epi.out_f32 = xf;
-    g.epi.out_bf16 = xb;
-    g.epi.out_bf16_pos = xpb;
-    g.epi.pos = pos; g.epi.pos_mod = pos_mod;
-    if (pos_extra) {  // last dummy layer: bf16(dummy + dummy_pos) rows go straight into Kc
-      g.epi.out_bf16_pos = pos_extra;
-      g.epi.pos_rowlim = pos_extra_rowlim;
-    }
-    FVTG_TRY(launch_gemm(st, w.ffh, nullptr, rows, 1024, 1024, L.ff2.w, g));
-  }
-  return FVTG_OK;
+  LayerArgs a = layer_args(L, rows, LAYER_SA, xf);
+  a.out_b = out_b;
+  a.out_pb = out_pb;
+  a.pos = pos;
+  a.pos_mod = pos_mod;
+  a.pos_rowlim = pos_rowlim;
+  return launch_layer(st, w.att, static_cast<const bf16*>(L.out_proj.w),
+                      static_cast<const bf16*>(L.ff1.w), static_cast<const bf16*>(L.ff2.w), a);
 }
 
-// One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396).
+// One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396):
+// attention over the constant [dummies ‖ text] keys, then the fused layer kernel.
 static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, const Ws& w, int B,
-                     int Lv, int S, const int* tlen) {
+                     int Lv, int S, const int* tlen, bool want_b) {
   const int rows = B * Lv;
   {
     AttnArgs a;
@@ -219,38 +210,12 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
     a.tsum = w.tsum;
     FVTG_TRY(launch_attention(st, a));
   }
-  {  // z = y + att Wo^T + bo (kept fp32 as the residual) ; tmp256 = bf16(LN1(z))
-    GemmArgs g = gemm_args(rows, 256, 256, 256);
-    g.epi.mode = EPI_ROW;
-    g.epi.bias = L.out_proj.b;
-    g.epi.res = w.Yf;
-    g.epi.gamma = L.norm1.g; g.epi.beta = L.norm1.b;
-    g.epi.f32_preln = 1;
-    g.epi.out_f32 = w.Yf;
-    g.epi.out_bf16 = w.tmp256;
-    FVTG_TRY(launch_gemm(st, w.att, nullptr, rows, 256, 256, L.out_proj.w, g));
-  }
-  {
-    GemmArgs g = gemm_args(rows, 1024, 256, 256);
-    g.epi.mode = EPI_TILE;
-    g.epi.bias = L.ff1.b;
-    g.epi.act = ACT_PRELU; g.epi.prelu = L.prelu;
-    g.epi.out = w.ffh; g.epi.ld_out = 1024;
-    FVTG_TRY(launch_gemm(st, w.tmp256, nullptr, rows, 256, 256, L.ff1.w, g));
-  }
-  {  // y = LN2(z + h W2^T + b2)
-    GemmArgs g = gemm_args(rows, 256, 256, 1024);
-    g.epi.mode = EPI_ROW;
-    g.epi.bias = L.ff2.b;
-    g.epi.res = w.Yf;
-    g.epi.gamma = L.norm2.g; g.epi.beta = L.norm2.b;
-    g.epi.out_f32 = w.Yf;
-    g.epi.out_bf16 = w.Yb;
-    g.epi.out_bf16_pos = w.YPb;
-    g.epi.pos = w.pos_v;
-    FVTG_TRY(launch_gemm(st, w.ffh, nullptr, rows, 1024, 1024, L.ff2.w, g));
-  }
-  return FVTG_OK;
+  LayerArgs a = layer_args(L, rows, LAYER_T2V, w.Yf);
+  a.out_b = want_b ? w.Yb : nullptr;
+  a.out_pb = w.YPb;
+  a.pos = w.pos_v;
+  return launch_layer(st, w.att, static_cast<const bf16*>(L.out_proj.w),
+                      static_cast<const bf16*>(L.ff1.w), static_cast<const bf16*>(L.ff2.w), a);
 }
 
 // LinearLayer x2 (model.py:99-110,782-789) for one modality.
@@ -289,36 +254,34 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
     GemmEpi e;
     memset(&e, 0, sizeof(e));
     e.rowmap = RM_TXT; e.rm_a = Lt; e.rm_b = S; e.rm_c = nd;
+    e.f32_blocked = 1;
     e.out_f32 = w.Xf; e.out_bf16 = w.Xb; e.out_bf16_pos = w.XPb; e.out_x1 = w.Kc;
     FVTG_TRY(in_proj(st, W.txt, w, txt, w.txt_b, B * Lt, c.t_dim, c.t_dim_pad, e));
   }
   {  // video
     GemmEpi e;
     memset(&e, 0, sizeof(e));
+    e.f32_blocked = 1;
     e.out_f32 = w.Yf; e.out_bf16 = w.Yb; e.out_bf16_pos = w.YPb; e.pos = w.pos_v;
     FVTG_TRY(in_proj(st, W.vid, w, vid, w.vid_b, B * Lv, c.v_dim, c.v_dim_pad, e));
   }
   for (int i = 0; i < c.dummy_layers; ++i) {
+    // the last dummy layer writes bf16(dummy + dummy_pos) straight into the key rows of Kc
     const bool last = i == c.dummy_layers - 1;
-    FVTG_TRY(sa_layer(st, W.dummy[i], w, B, S, w.Xf, w.Xb, w.XPb, w.pos_d, S, tlen, nd,
-                      last ? w.Kc : nullptr, nd));
+    FVTG_TRY(sa_layer(st, W.dummy[i], w, B, S, w.Xf, w.Xb, w.XPb, last ? nullptr : w.Xb,
+                      last ? w.Kc : w.XPb, w.pos_d, S, last ? nd : 0, tlen, nd));
   }
-  if (dummy_tokens) {
-    FVTG_CUDA_OK(cudaMemcpy2DAsync(dummy_tokens, sizeof(float) * nd * 256, w.Xf,
-                                   sizeof(float) * S * 256, sizeof(float) * nd * 256, B,
-                                   cudaMemcpyDeviceToDevice, st));
-    count_launch();
+  if (dummy_tokens) FVTG_TRY(launch_unblock(st, w.Xf, dummy_tokens, B, S, nd));
+  for (int i = 0; i < c.t2v_layers; ++i)
+    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1));
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const bool last = i == c.enc_layers - 1;
+    FVTG_TRY(sa_layer(st, W.enc[i], w, B, Lv, w.Yf, w.Yb, w.YPb, last ? nullptr : w.Yb,
+                      last ? nullptr : w.YPb, w.pos_v, 0, 0, vlen, 0));
   }
-  for (int i = 0; i < c.t2v_layers; ++i) FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen));
-  for (int i = 0; i < c.enc_layers; ++i)
-    FVTG_TRY(sa_layer(st, W.enc[i], w, B, Lv, w.Yf, w.Yb, w.YPb, w.pos_v, 0, vlen, 0, nullptr, 0));
   FVTG_TRY(launch_saliency(st, w.Yf, vlen, W.sal_w1, W.sal_b1, W.sal_w2t, W.sal_b2, w.tsum,
                            c.t2v_layers > 0 ? c.t2v_layers : 1, saliency, t2v, B, Lv));
-  if (video_emb) {
-    FVTG_CUDA_OK(cudaMemcpyAsync(video_emb, w.Yf, sizeof(float) * B * Lv * 256,
-                                 cudaMemcpyDeviceToDevice, st));
-    count_launch();
-  }
+  if (video_emb) FVTG_TRY(launch_unblock(st, w.Yf, video_emb, B * Lv, 1, 1));
   return FVTG_OK;
 }
 
@@ -369,13 +332,13 @@ static int score_head(cudaStream_t st, const FvtgCfg& c, const FvtgScoreHead& H,
 }
 
 static int pyramid_heads_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W, const Ws& w,
-                               int B, int Lv, const float* F, const int* vlen, float* cls,
-                               float* conf, float* coord) {
+                               int B, int Lv, const float* F, bool f_blocked, const int* vlen,
+                               float* cls, float* conf, float* coord) {
   PyrGeo geo = make_geo(c, Lv, vlen);
   FVTG_CUDA_OK(cudaMemsetAsync(w.H1, 0, static_cast<size_t>(B) * geo.PH1 * 256 * sizeof(bf16), st));
   FVTG_CUDA_OK(cudaMemsetAsync(w.H2, 0, static_cast<size_t>(B) * geo.PH2 * 256 * sizeof(bf16), st));
   count_launch(2);
-  FVTG_TRY(launch_level0(st, F, w.chain0, w.H1, w.H2, B, Lv, geo));
+  FVTG_TRY(launch_level0(st, F, w.chain0, w.H1, w.H2, B, Lv, geo, f_blocked));
   // Temporal Feature Layering (blocks.py:52-70): level l = l strided convs from ReLU(F), own weights
   for (int l = 1; l < geo.nlev; ++l) {
     const bf16* src = w.chain0;
@@ -523,7 +486,7 @@ int32_t fvtg_pyramid_heads_fwd(const FvtgCfg* cfg, const FvtgWeights* w, int32_t
   for (int b0 = 0; b0 < B; b0 += bc) {
     const int nb = B - b0 < bc ? B - b0 : bc;
     FVTG_TRY(pyramid_heads_chunk(st, *cfg, *w, ws, nb, Lv,
-                                 video_emb + static_cast<size_t>(b0) * Lv * 256, vid_len + b0,
+                                 video_emb + static_cast<size_t>(b0) * Lv * 256, false, vid_len + b0,
                                  out->cls_logit + static_cast<size_t>(b0) * g0.n_max,
                                  out->conf_logit + static_cast<size_t>(b0) * g0.n_max,
                                  out->coord + static_cast<size_t>(b0) * g0.n_max * 2));
@@ -598,7 +561,7 @@ int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* 
     float* cls = keep_heads ? hout->cls_logit + static_cast<size_t>(b0) * g0.n_max : ws.cls;
     float* conf = keep_heads ? hout->conf_logit + static_cast<size_t>(b0) * g0.n_max : ws.conf;
     float* coord = keep_heads ? hout->coord + static_cast<size_t>(b0) * g0.n_max * 2 : ws.coord;
-    FVTG_TRY(pyramid_heads_chunk(st, *cfg, *w, ws, nb, Lv, ws.Yf, in->vid_len + b0, cls, conf, coord));
+    FVTG_TRY(pyramid_heads_chunk(st, *cfg, *w, ws, nb, Lv, ws.Yf, true, in->vid_len + b0, cls, conf, coord));
     FvtgDecodeOut d = *dout;
     const int tk = p.topk;
     if (d.boundary) d.boundary += static_cast<size_t>(b0) * tk * 3;

@@ -93,8 +93,33 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, pitch;
+  uint32_t box_rows, box_cols;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && pitch == o.pitch &&
+           box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct TmapEntry { TmapKey key; CUtensorMap map; };
+
+// Descriptors are pure functions of (pointer, geometry): the same few hundred recur every step
+// (workspace carving is deterministic), so encoding is cached per thread.
+static std::vector<TmapEntry>& tmap_cache() {
+  static thread_local std::vector<TmapEntry> c;
+  return c;
+}
+
 int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                    uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{base, rows, cols, pitch_elems, box_rows, box_cols};
+  std::vector<TmapEntry>& cache = tmap_cache();
+  for (const TmapEntry& e : cache)
+    if (e.key == key) {
+      *map = e.map;
+      return FVTG_OK;
+    }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(FVTG_ELAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((pitch_elems * 2) & 15))
@@ -110,6 +135,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
     return fail(FVTG_ELAUNCH, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu pitch=%llu",
                 (int)r, (unsigned long long)rows, (unsigned long long)cols,
                 (unsigned long long)pitch_elems);
+  if (cache.size() >= 1024) cache.clear();
+  cache.push_back(TmapEntry{key, *map});
   return FVTG_OK;
 }
 

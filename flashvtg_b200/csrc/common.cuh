@@ -53,7 +53,7 @@ inline void count_launch(int n = 1) { host_state().launches += n; }
 // Bench hook (fvtg_prof_enable / fvtg_prof_collect): when enabled every launcher brackets its
 // kernel with a CUDA event pair on the launching stream, so bench.py can time each kernel class
 // live (the roofline numerator) without a profiler attached.  Off by default: zero cost.
-enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LNCAST = 2, PC_DECODE = 3, PC_OTHER = 4, PC_COUNT = 5 };
+enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LNCAST = 2, PC_DECODE = 3, PC_OTHER = 4, PC_LAYER = 5, PC_COUNT = 6 };
 bool prof_on();
 void prof_begin(cudaStream_t st, int cls);
 void prof_end(cudaStream_t st);
@@ -87,6 +87,14 @@ struct PyrGeo {
   int o1[FVTG_MAX_LEVELS];
   const int* vlen;  // [Bc] true video lengths of this chunk
 };
+
+// fp32 residual streams (video stream Y, dummy/text stream X, the sine table) are kept in a
+// tile-blocked layout [row/128][col/4][row%128][4]: the tcgen05 epilogues own one row per thread
+// (TMEM lane == row), so consecutive lanes touch consecutive 16-byte groups - every residual load
+// and store is fully coalesced without staging through shared memory.
+__host__ __device__ inline size_t blk_off(size_t row, int col) {
+  return ((row >> 7) * 64 + static_cast<size_t>(col >> 2)) * 512 + (row & 127) * 4 + (col & 3);
+}
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }

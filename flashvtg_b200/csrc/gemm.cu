@@ -86,10 +86,27 @@ __device__ __forceinline__ void store_bf16x32(bf16* dst, const float* y) {
     p[q] = u;
   }
 }
-__device__ __forceinline__ void store_f32x32(float* dst, const float* y) {
-  float4* p = reinterpret_cast<float4*>(dst);
+// 32 consecutive columns of one row, starting at column c0: row-major (stride 4 floats between the
+// 16-byte groups) or tile-blocked (stride 512 floats).
+__device__ __forceinline__ void store_f32x32(float* base, size_t row, int c0, bool blocked,
+                                             const float* y) {
+  float* p = blocked ? base + blk_off(row, c0) : base + row * 256 + c0;
+  const int stride = blocked ? 512 : 4;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) p[q] = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(p + q * stride) =
+        make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+}
+__device__ __forceinline__ void add_f32x32(const float* base, size_t row, int c0, bool blocked,
+                                           float* v) {
+  const float* p = blocked ? base + blk_off(row, c0) : base + row * 256 + c0;
+  const int stride = blocked ? 512 : 4;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 r4 = *reinterpret_cast<const float4*>(p + q * stride);
+    v[q * 4 + 0] += r4.x; v[q * 4 + 1] += r4.y;
+    v[q * 4 + 2] += r4.z; v[q * 4 + 3] += r4.w;
+  }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -227,7 +244,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (e.mode == EPI_ROW) {
         const bool ln = e.gamma != nullptr;
         float mean = 0.f, rstd = 1.f;
-        const float* resp = (e.res && ri.inb) ? e.res + static_cast<size_t>(row) * 256 : nullptr;
+        const bool has_res = e.res && ri.inb;
+        const bool blk = e.f32_blocked != 0;
         if (ln) {
           float s1 = 0.f, s2 = 0.f, shift = 0.f;
           for (int c0 = 0; c0 < 256; c0 += 32) {
@@ -235,14 +253,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) + s_bias[c0 + j];
-            if (resp) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 r4 = *reinterpret_cast<const float4*>(resp + c0 + q * 4);
-                v[q * 4 + 0] += r4.x; v[q * 4 + 1] += r4.y;
-                v[q * 4 + 2] += r4.z; v[q * 4 + 3] += r4.w;
-              }
-            }
+            if (has_res) add_f32x32(e.res, row, c0, blk, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, e.prelu);
             if (c0 == 0) shift = v[0];
@@ -252,8 +263,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               s1 += d;
               s2 += d * d;
             }
-            if (e.out_f32 && e.f32_preln && ri.inb)
-              store_f32x32(e.out_f32 + static_cast<size_t>(ri.dst) * 256 + c0, v);
+            if (e.out_f32 && e.f32_preln && ri.inb) store_f32x32(e.out_f32, ri.dst, c0, blk, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(v[j]);
             tmem_st32(tacc + c0, u);
@@ -277,14 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) + s_bias[c0 + j];
-            if (resp) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 r4 = *reinterpret_cast<const float4*>(resp + c0 + q * 4);
-                v[q * 4 + 0] += r4.x; v[q * 4 + 1] += r4.y;
-                v[q * 4 + 2] += r4.z; v[q * 4 + 3] += r4.w;
-              }
-            }
+            if (has_res) add_f32x32(e.res, row, c0, blk, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, e.prelu);
           }
@@ -298,7 +301,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (ri.inb) {
             const size_t o = static_cast<size_t>(ri.dst) * 256 + c0;
-            if (e.out_f32 && !(ln && e.f32_preln)) store_f32x32(e.out_f32 + o, v);
+            if (e.out_f32 && !(ln && e.f32_preln)) store_f32x32(e.out_f32, ri.dst, c0, blk, v);
             if (e.out_bf16) store_bf16x32(e.out_bf16 + o, v);
             if (e.rowmap == RM_TXT) {
               if (e.out_x1) store_bf16x32(e.out_x1 + static_cast<size_t>(ri.x1) * 256 + c0, v);
@@ -307,15 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (e.out_x2) store_bf16x32(e.out_x2 + static_cast<size_t>(ri.x2) * 256 + c0, v);
             }
             if (st_pos) {
-              if (e.pos) {
-                const float* pp = e.pos + static_cast<size_t>(prow) * 256 + c0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 p4 = *reinterpret_cast<const float4*>(pp + q * 4);
-                  v[q * 4 + 0] += p4.x; v[q * 4 + 1] += p4.y;
-                  v[q * 4 + 2] += p4.z; v[q * 4 + 3] += p4.w;
-                }
-              }
+              if (e.pos) add_f32x32(e.pos, prow, c0, blk && e.pos_mod <= 0, v);
               store_bf16x32(e.out_bf16_pos + o, v);
             }
           }

@@ -46,7 +46,8 @@ struct GemmEpi {
   const float* gamma;  // LayerNorm weight or null (no LN)
   const float* beta;
   int post_relu;       // ReLU after LayerNorm (pyramid)
-  int f32_preln;       // out_f32 receives the pre-LayerNorm sum (T2V layers keep it as residual)
+  int f32_preln;       // out_f32 receives the pre-LayerNorm sum
+  int f32_blocked;     // res / out_f32 / per-row pos use the tile-blocked layout (blk_off)
   float* out_f32;      // [rows][256] or null
   bf16* out_bf16;      // [rows][256] or null
   bf16* out_bf16_pos;  // [rows][256] or null: bf16(y + pos[row])

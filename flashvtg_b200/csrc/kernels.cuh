@@ -11,16 +11,36 @@ namespace fvtg {
 int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const float* beta,
                    bf16* out, int rows, int dim, int dim_pad);
 // Sine position table (position_encoding.py:61-72) for every video row of the chunk:
-// pos fp32 [B*Lv][256]; rows >= vlen[b] are zero.
+// pos fp32 [B*Lv][256] in the tile-blocked layout; rows >= vlen[b] are zero.
 int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv);
-// Initial dummy-encoder stream: rows [b*S + j], j < nd, of X (fp32), Xb = bf16(X),
+// Initial dummy-encoder stream: rows [b*S + j], j < nd, of X (fp32, tile-blocked), Xb = bf16(X),
 // XPb = bf16(X + dummy_pos); and the [dummy_pos ‖ 0] position table pos_d fp32 [S][256].
 int launch_fill_dummy(cudaStream_t st, const float* dtok, const float* dpos, float* X, bf16* Xb,
                       bf16* XPb, float* pos_d, int B, int S, int nd);
 // Pyramid level 0 (blocks.py:35, in-place ReLU): F fp32 [B*Lv][256] -> relu -> bf16 into the chain
 // buffer (pitch P0, pad rows zero) and the two head layouts H1 / H2.
 int launch_level0(cudaStream_t st, const float* F, bf16* chain0, bf16* H1, bf16* H2, int B, int Lv,
-                  const PyrGeo& geo);
+                  const PyrGeo& geo, bool blocked);
+
+// ---- layer.cu : fused out_proj + LN1 + FFN + LN2 (tcgen05, hidden activations stay on-chip) ------
+enum LayerMode { LAYER_T2V = 0, LAYER_SA = 1 };
+struct LayerArgs {
+  int M;       // rows of the stream (B * L)
+  int mode;    // LAYER_T2V: FFN residual is the pre-LN1 sum ; LAYER_SA: it is the LN1 output
+  float prelu;
+  const float *bo, *g1, *be1, *b1, *b2, *g2, *be2;
+  float* yf;         // fp32 residual stream, tile-blocked (blk_off), read then overwritten
+  bf16* out_b;       // bf16(y) [M][256] row-major or null
+  bf16* out_pb;      // bf16(y + pos) [M][256] or null
+  const float* pos;  // pos_mod == 0: tile-blocked per-row table ; > 0: row-major [pos_mod][256] ; null = 0
+  int pos_mod;
+  int pos_rowlim;    // > 0: out_pb only for rows with row % pos_mod < pos_rowlim
+};
+int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
+                 const LayerArgs& args);
+
+// fp32 tile-blocked rows -> row-major fp32: dst[(b * rows_out + j)][256] = src row (b * rows_in + j), j < rows_out
+int launch_unblock(cudaStream_t st, const float* src_blk, float* dst, int B, int rows_in, int rows_out);
 
 // ---- attn.cu : per-(video, head) attention on legacy warp MMA ----------------------------------
 struct AttnArgs {
@@ -37,7 +57,8 @@ struct AttnArgs {
 int launch_attention(cudaStream_t st, const AttnArgs& a);
 
 // ---- saliency.cu ---------------------------------------------------------------------------
-// saliency (transformer.py:106-113) + t2vattnvalues finalisation (model.py:215-216).
+// saliency (transformer.py:106-113) + t2vattnvalues finalisation (model.py:215-216).  F is the
+// tile-blocked fp32 stream.
 int launch_saliency(cudaStream_t st, const float* F, const int* vlen, const float* w1,
                     const float* b1, const float* w2t, const float* b2, const float* tsum,
                     int t2v_layers, float* sal_out, float* t2v_out, int B, int Lv);

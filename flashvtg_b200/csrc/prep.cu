@@ -115,7 +115,7 @@ __global__ void posenc_kernel(float* __restrict__ pos, const int* __restrict__ v
     const float a = e / w;
     v = (c & 1) ? cosf(a) : sinf(a);
   }
-  pos[static_cast<size_t>(row) * 256 + c] = v;
+  pos[blk_off(row, c)] = v;
 }
 
 int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv) {
@@ -137,7 +137,7 @@ __global__ void fill_dummy_kernel(const float* __restrict__ dtok, const float* _
   const float t = dtok[j * 256 + c], p = dpos[j * 256 + c];
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const size_t o = (static_cast<size_t>(b) * S + j) * 256 + c;
-    X[o] = t;
+    X[blk_off(static_cast<size_t>(b) * S + j, c)] = t;
     Xb[o] = __float2bfloat16(t);
     XPb[o] = __float2bfloat16(t + p);
   }
@@ -155,7 +155,7 @@ int launch_fill_dummy(cudaStream_t st, const float* dtok, const float* dpos, flo
 // thread = (chain row, 8 channels)
 __global__ void level0_kernel(const float* __restrict__ F, bf16* __restrict__ chain0,
                               bf16* __restrict__ H1, bf16* __restrict__ H2, int B, int Lv,
-                              PyrGeo geo) {
+                              PyrGeo geo, int blocked) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = t >> 5, c8 = (t & 31) * 8;
   if (row >= B * geo.P0) return;
@@ -164,8 +164,16 @@ __global__ void level0_kernel(const float* __restrict__ F, bf16* __restrict__ ch
   uint4 o = make_uint4(0, 0, 0, 0);
   const bool valid = i < vl;
   if (valid) {
-    const float4* src = reinterpret_cast<const float4*>(F + (static_cast<size_t>(b) * Lv + i) * 256 + c8);
-    const float4 a = __ldg(src), c = __ldg(src + 1);
+    const size_t frow = static_cast<size_t>(b) * Lv + i;
+    float4 a, c;
+    if (blocked) {
+      a = __ldg(reinterpret_cast<const float4*>(F + blk_off(frow, c8)));
+      c = __ldg(reinterpret_cast<const float4*>(F + blk_off(frow, c8 + 4)));
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(F + frow * 256 + c8);
+      a = __ldg(src);
+      c = __ldg(src + 1);
+    }
     o.x = pack_bf16(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
     o.y = pack_bf16(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
     o.z = pack_bf16(fmaxf(c.x, 0.f), fmaxf(c.y, 0.f));
@@ -181,13 +189,34 @@ __global__ void level0_kernel(const float* __restrict__ F, bf16* __restrict__ ch
 }
 
 int launch_level0(cudaStream_t st, const float* F, bf16* chain0, bf16* H1, bf16* H2, int B, int Lv,
-                  const PyrGeo& geo) {
+                  const PyrGeo& geo, bool blocked) {
   const long long threads = static_cast<long long>(B) * geo.P0 * 32;
   if (threads <= 0) return FVTG_OK;
   const int grid = static_cast<int>((threads + 255) / 256);
   ProfScope prof(st, PC_OTHER);
-  level0_kernel<<<grid, 256, 0, st>>>(F, chain0, H1, H2, B, Lv, geo);
+  level0_kernel<<<grid, 256, 0, st>>>(F, chain0, H1, H2, B, Lv, geo, blocked ? 1 : 0);
   FVTG_LAUNCH_CHECK("level0_kernel");
+  return FVTG_OK;
+}
+
+// thread = (output row, 4 columns)
+__global__ void unblock_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
+                               int rows_in, int rows_out) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long orow = t >> 6;
+  const int c4 = static_cast<int>(t & 63) * 4;
+  if (orow >= static_cast<long long>(B) * rows_out) return;
+  const long long b = orow / rows_out, j = orow - b * rows_out;
+  const float4 v = *reinterpret_cast<const float4*>(src + blk_off(static_cast<size_t>(b * rows_in + j), c4));
+  *reinterpret_cast<float4*>(dst + orow * 256 + c4) = v;
+}
+
+int launch_unblock(cudaStream_t st, const float* src_blk, float* dst, int B, int rows_in, int rows_out) {
+  const long long threads = static_cast<long long>(B) * rows_out * 64;
+  if (threads <= 0) return FVTG_OK;
+  ProfScope prof(st, PC_OTHER);
+  unblock_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(src_blk, dst, B, rows_in, rows_out);
+  FVTG_LAUNCH_CHECK("unblock_kernel");
   return FVTG_OK;
 }
 

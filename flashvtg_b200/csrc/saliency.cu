@@ -29,8 +29,8 @@ saliency_kernel(const float* __restrict__ F, const int* __restrict__ vlen,
     float acc = 0.f;
     if (b < B) {
       const int len = vlen[b];
-      const float* f = F + static_cast<size_t>(b) * Lv * 256 + c;
-      for (int i = 0; i < len; ++i) acc += f[static_cast<size_t>(i) * 256];
+      const size_t r0 = static_cast<size_t>(b) * Lv;
+      for (int i = 0; i < len; ++i) acc += F[blk_off(r0 + i, c)];
       acc /= static_cast<float>(len > 0 ? len : 1);
     }
     s_g[v][c] = acc;
@@ -83,9 +83,8 @@ saliency_kernel(const float* __restrict__ F, const int* __restrict__ vlen,
       const size_t row = static_cast<size_t>(b) * Lv + i;
       float acc = 0.f;
       if (i < len) {
-        const float* f = F + row * 256;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc += f[lane + 32 * q] * s_w[v][lane + 32 * q];
+        for (int q = 0; q < 8; ++q) acc += F[blk_off(row, lane + 32 * q)] * s_w[v][lane + 32 * q];
         acc = warp_sum(acc);
       }
       if (lane == 0) {

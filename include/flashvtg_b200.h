@@ -232,9 +232,10 @@ int32_t fvtg_abi_version(void);
 
 /* Bench hook.  fvtg_prof_enable(1): every kernel launched by this thread's later fvtg_* calls is
  * bracketed by a CUDA event pair on its stream.  fvtg_prof_collect waits for them and returns, per
- * kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm+cast staging, 3 decode/NMS, 4 other),
+ * kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm+cast staging, 3 decode/NMS, 4 other,
+ * 5 fused tcgen05 transformer-layer kernel),
  * the summed device time in ms and the launch count since the last collect. */
-#define FVTG_PROF_CLASSES 5
+#define FVTG_PROF_CLASSES 6
 void fvtg_prof_enable(int32_t on);
 int32_t fvtg_prof_collect(double* ms, int64_t* launches, int32_t n_classes);
 
