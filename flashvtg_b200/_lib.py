@@ -118,6 +118,7 @@ SIGNATURES = {
     "fvtg_last_launch_count": (C.c_int64, []),
     "fvtg_last_error": (C.c_char_p, []),
     "fvtg_abi_version": (i32, []),
+    "fvtg_dbg_set_trace": (None, [vp]),
     "fvtg_prof_enable": (None, [i32]),
     "fvtg_prof_collect": (i32, [vp, vp, i32]),
     "fvtg_dbg_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),

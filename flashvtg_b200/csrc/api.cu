@@ -153,6 +153,7 @@ static LayerArgs layer_args(const FvtgEncLayer& L, int rows, int mode, float* yf
   a.b2 = L.ff2.b;
   a.g2 = L.norm2.g; a.be2 = L.norm2.b;
   a.yf = yf;
+  a.trace = dbg_trace();
   return a;
 }
 

@@ -35,6 +35,7 @@ struct LayerArgs {
   const float* pos;  // pos_mod == 0: tile-blocked per-row table ; > 0: row-major [pos_mod][256] ; null = 0
   int pos_mod;
   int pos_rowlim;    // > 0: out_pb only for rows with row % pos_mod < pos_rowlim
+  long long* trace;  // debug: per-phase clock64 stamps of CTA 0 (fvtg_dbg_set_trace), null in production
 };
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args);

@@ -38,6 +38,13 @@ constexpr int LK_PAR_FLOATS = 256 * 3 + 1024 + 256 * 3;
 constexpr int LK_SMEM_BYTES = LK_OFF_PAR + LK_PAR_FLOATS * 4 + 1024 /*align slack*/;
 static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 KB limit");
 
+// trace slots: [role 0 MMA / 1 epilogue][tile it < 8][event < 32]
+#define LK_TRACE(role, ev)                                                              \
+  do {                                                                                  \
+    if (g.trace && blockIdx.x == 0 && it < 8)                                           \
+      g.trace[((role) * 8 + it) * 32 + (ev)] = clock64();                               \
+  } while (0)
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // byte offset of 16-byte chunk c (0..7) of row r inside one SWIZZLE_128B unit
@@ -219,21 +226,30 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               unit(tmem + nh * 128, sH_u + buf * 2 * LK_UNIT + kb2 * LK_UNIT, true);
           umma_commit(&h_empty[buf]);
         };
+        LK_TRACE(0, 0);
         mbar_wait(z_empty, (it & 1) ^ 1);
+        LK_TRACE(0, 1);
         mbar_wait(a_full, it & 1);
         tc_fence_after();
+        LK_TRACE(0, 2);
         for (int kb = 0; kb < 4; ++kb)
           for (int nh = 0; nh < 2; ++nh) unit(tmem + nh * 128, sA_u + kb * LK_UNIT, kb > 0);
         umma_commit(z1_full);
+        LK_TRACE(0, 3);
         mbar_wait(ln_ready, it & 1);
         tc_fence_after();
+        LK_TRACE(0, 4);
         ff1(0);
         ff1(1);
+        LK_TRACE(0, 5);
         for (int p = 0; p < 8; ++p) {
           ff2(p);
+          LK_TRACE(0, 6 + 2 * p);
           if (p + 2 < 8) ff1(p + 2);
+          LK_TRACE(0, 7 + 2 * p);
         }
         umma_commit(z2_full);
+        LK_TRACE(0, 22);
       }
     }
   } else if (warp >= 4) {
@@ -253,8 +269,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float* yblk = g.yf + static_cast<size_t>(tile) * (128 * 256) + r * 4;
 
       // ---- epilogue 1: z = D_z + bo + x ; LayerNorm1 -> sA ; residual back into D_z ----------
+      const bool tr = (warp == 4 && lane == 0);
+      if (tr) LK_TRACE(1, 0);
       mbar_wait(z1_full, it & 1);
       tc_fence_after();
+      if (tr) LK_TRACE(1, 1);
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -284,6 +303,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_st32(tmem + lane_addr + c0, u);
       }
       tmem_st_wait();
+      if (tr) LK_TRACE(1, 2);
       s_stat[hf * 128 + r] = make_float2(shift + s1 * (1.f / 128.f), s2 - s1 * s1 * (1.f / 128.f));
       epi_bar_sync();
       float mean, rstd;
@@ -314,6 +334,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ln_ready);
+      if (tr) LK_TRACE(1, 3);
 
       // ---- epilogue 2 (x8): hidden piece = PReLU(D_h + b1) -> sH ------------------------------
 #pragma unroll 1
@@ -323,6 +344,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&hacc_full[buf], n & 1u);
         mbar_wait(&h_empty[buf], (n & 1u) ^ 1u);
         tc_fence_after();
+        if (tr) LK_TRACE(1, 4 + 2 * p);
         uint8_t* hu = sH + buf * 2 * LK_UNIT + hf * LK_UNIT;  // k-block hf of the piece
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -341,11 +363,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_ready[buf]);
+        if (tr) LK_TRACE(1, 5 + 2 * p);
       }
 
       // ---- final epilogue: y = LayerNorm2(D_z + b2) -> residual stream / bf16 operands --------
       mbar_wait(z2_full, it & 1);
       tc_fence_after();
+      if (tr) LK_TRACE(1, 20);
       shift = 0.f; s1 = 0.f; s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -362,6 +386,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       s_stat[256 + hf * 128 + r] = make_float2(shift + s1 * (1.f / 128.f), s2 - s1 * s1 * (1.f / 128.f));
       epi_bar_sync();
+      if (tr) LK_TRACE(1, 21);
       {
         const float2 a = s_stat[256 + r], b = s_stat[256 + 128 + r];
         const float dm = a.x - b.x;
@@ -417,6 +442,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(z_empty);
+      if (tr) LK_TRACE(1, 22);
     }
   }
 

@@ -239,6 +239,10 @@ int32_t fvtg_abi_version(void);
 void fvtg_prof_enable(int32_t on);
 int32_t fvtg_prof_collect(double* ms, int64_t* launches, int32_t n_classes);
 
+/* Debug hook: device buffer (>= 4096 int64) that the fused layer kernel's CTA 0 fills with clock64
+ * stamps per pipeline phase (tools/trace_layer.py); null (default) disables tracing. */
+void fvtg_dbg_set_trace(void* device_buf);
+
 /* Test hook: out = act(A[M][K] * W[N][K]^T + bias) through the production tcgen05 GEMM.
  * A, W bf16 (K multiple of 64, N multiple of 128).  N == 256: out is fp32 [M][256] (full-row
  * epilogue); otherwise out is bf16 [M][N] (tile epilogue).  act: 0 none, 1 relu. */
