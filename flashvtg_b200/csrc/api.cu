@@ -55,7 +55,7 @@ struct Carver {
 struct Ws {
   // fusion
   bf16 *vid_b, *txt_b, *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
-  float *Xf, *Yf, *pos_v, *pos_d, *tsum;
+  float *Xf, *Yf, *pos_v, *pos_d, *tsum, *sal_scratch;
   // pyramid + heads
   bf16 *chain0, *chainA, *chainB, *H1, *H2, *hA, *hB, *mA, *mB;
   // per-chunk head logits when the caller does not want them
@@ -85,7 +85,8 @@ static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws*
   t.qkv = k.take<bf16>(Rmax * 768);
   t.att = k.take<bf16>(Rmax * 256);
   t.ffh = k.take<bf16>(Rmax * 1024);
-  t.tsum = k.take<float>(8 * Rv);
+  t.tsum = k.take<float>(8 * Rv * (c.t2v_layers > 0 ? c.t2v_layers : 1));  // [layer][head][row]
+  t.sal_scratch = k.take<float>(static_cast<size_t>(Bc) * 513 + 64);
   const size_t Rc = static_cast<size_t>(Bc) * g.P0;
   t.chain0 = k.take<bf16>(Rc * 256);
   t.chainA = k.take<bf16>(Rc / 2 * 256 + 256);
@@ -197,7 +198,7 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
 // One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396):
 // attention over the constant [dummies ‖ text] keys, then the fused layer kernel.
 static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, const Ws& w, int B,
-                     int Lv, int S, const int* tlen, bool want_b) {
+                     int Lv, int S, const int* tlen, bool want_b, int layer) {
   const int rows = B * Lv;
   {
     AttnArgs a;
@@ -208,7 +209,7 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
     a.out = w.att;
     a.B = B; a.Lq = Lv; a.Lk = S;
     a.klen_src = tlen; a.kbase = c.num_dummies; a.v_first = c.num_dummies;
-    a.tsum = w.tsum;
+    a.tsum = w.tsum + static_cast<size_t>(layer) * 8 * B * Lv;
     FVTG_TRY(launch_attention(st, a));
   }
   LayerArgs a = layer_args(L, rows, LAYER_T2V, w.Yf);
@@ -249,8 +250,6 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
   const int nd = c.num_dummies, S = nd + Lt;
   FVTG_TRY(launch_posenc(st, w.pos_v, vlen, B, Lv));
   FVTG_TRY(launch_fill_dummy(st, W.dummy_tok, W.dummy_pos, w.Xf, w.Xb, w.XPb, w.pos_d, B, S, nd));
-  FVTG_CUDA_OK(cudaMemsetAsync(w.tsum, 0, sizeof(float) * 8 * B * Lv, st));
-  count_launch();
   {  // text: rows scattered into the [dummies ‖ text] stream, plus the constant text keys/values
     GemmEpi e;
     memset(&e, 0, sizeof(e));
@@ -274,14 +273,14 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
   }
   if (dummy_tokens) FVTG_TRY(launch_unblock(st, w.Xf, dummy_tokens, B, S, nd));
   for (int i = 0; i < c.t2v_layers; ++i)
-    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1));
+    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1, i));
   for (int i = 0; i < c.enc_layers; ++i) {
     const bool last = i == c.enc_layers - 1;
     FVTG_TRY(sa_layer(st, W.enc[i], w, B, Lv, w.Yf, w.Yb, w.YPb, last ? nullptr : w.Yb,
                       last ? nullptr : w.YPb, w.pos_v, 0, 0, vlen, 0));
   }
   FVTG_TRY(launch_saliency(st, w.Yf, vlen, W.sal_w1, W.sal_b1, W.sal_w2t, W.sal_b2, w.tsum,
-                           c.t2v_layers > 0 ? c.t2v_layers : 1, saliency, t2v, B, Lv));
+                           c.t2v_layers, w.sal_scratch, saliency, t2v, B, Lv));
   if (video_emb) FVTG_TRY(launch_unblock(st, w.Yf, video_emb, B * Lv, 1, 1));
   return FVTG_OK;
 }

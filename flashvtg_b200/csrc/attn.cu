@@ -137,7 +137,7 @@ attention_kernel(const AttnArgs a, const int Lkpad) {
       for (int nt2 = 0; nt2 < 4; ++nt2)
         *reinterpret_cast<uint32_t*>(dst + nt2 * 8) = pack_bf16(o[nt2][0] * i0, o[nt2][1] * i0);
       if (a.tsum && t == 0)
-        a.tsum[static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq + r0] += ts0 * i0;
+        a.tsum[static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq + r0] = ts0 * i0;
     }
     if (r1 < a.Lq) {
       bf16* dst = a.out + (static_cast<size_t>(b) * a.Lq + r1) * 256 + h * 32 + 2 * t;
@@ -145,192 +145,215 @@ attention_kernel(const AttnArgs a, const int Lkpad) {
       for (int nt2 = 0; nt2 < 4; ++nt2)
         *reinterpret_cast<uint32_t*>(dst + nt2 * 8) = pack_bf16(o[nt2][2] * i1, o[nt2][3] * i1);
       if (a.tsum && t == 0)
-        a.tsum[static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq + r1] += ts1 * i1;
+        a.tsum[static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq + r1] = ts1 * i1;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Short sequences (everything QVHighlights-sized): one CTA per video, one warp per head.  The
-// video's Q / K / V rows are staged once with coalesced 16-byte cp.async (row pitch 528 B keeps
-// ldmatrix conflict-free), the whole score row lives in registers (no online softmax), the output
-// tile is written back through shared memory so that global stores are 16 bytes per lane.
-constexpr int AV_PITCH = 264;      // bf16 elements per staged row (256 + 8 pad)
-constexpr int AV_MAX_NT = 20;      // up to 160 keys
+// Short sequences (everything QVHighlights-sized): one CTA per (video, group of 4 heads), 8 warps =
+// 4 heads x 2 interleaved m-tile groups.  The 128-column slices of the video's Q / K / V rows are
+// staged once with coalesced 16-byte cp.async (row pitch 272 B keeps ldmatrix conflict-free), the
+// whole score row lives in registers (no online softmax), the output tile goes back through
+// shared memory so that global stores are 16 bytes per lane.  ~65 KB of shared memory and <= 85
+// registers keep 3 CTAs (24 warps) per SM: the kernel is issue-bound on the softmax, not on MMA.
+constexpr int AV_PITCH = 136;  // bf16 elements per staged row (4 heads x 32 + 8 pad)
 
-template <bool KV_SHARED>
-__global__ void __launch_bounds__(256)
-attn_video_kernel(const AttnArgs a, const int LqPad, const int LkPad) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NT, bool KV_SHARED>
+__global__ void __launch_bounds__(256, (NT <= 10 ? 3 : 2))
+attn_video_kernel(const AttnArgs a, const int LqPad) {
+  constexpr int LkPad = NT * 8;
   extern __shared__ __align__(16) uint8_t av_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(av_smem);
   bf16* sK = sQ + static_cast<size_t>(LqPad) * AV_PITCH;
   bf16* sV = KV_SHARED ? sK : sK + static_cast<size_t>(LkPad) * AV_PITCH;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x >> 1, hg = blockIdx.x & 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   int klen = a.kbase + a.klen_src[b];
   if (klen > a.Lk) klen = a.Lk;
+  const int col0 = hg * 128;
 
-  // ---- stage: 32 x 16-byte chunks per row -------------------------------------------------
+  // ---- stage: 16 x 16-byte chunks per row ---------------------------------------------------
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  for (int idx = tid; idx < LqPad * 32; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;
+  for (int idx = tid; idx < LqPad * 16; idx += 256) {
+    const int r = idx >> 4, c = idx & 15;
     bf16* dst = sQ + r * AV_PITCH + c * 8;
-    if (r < a.Lq) cp_async16(smem_u32(dst), a.q + (static_cast<size_t>(b) * a.Lq + r) * a.ldq + c * 8);
-    else *reinterpret_cast<uint4*>(dst) = zero4;
+    if (r < a.Lq)
+      cp_async16(smem_u32(dst), a.q + (static_cast<size_t>(b) * a.Lq + r) * a.ldq + col0 + c * 8);
+    else
+      *reinterpret_cast<uint4*>(dst) = zero4;
   }
-  for (int idx = tid; idx < LkPad * 32; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;
+  for (int idx = tid; idx < LkPad * 16; idx += 256) {
+    const int r = idx >> 4, c = idx & 15;
     bf16* dk = sK + r * AV_PITCH + c * 8;
     const size_t grow = static_cast<size_t>(b) * a.Lk + r;
-    if (r < klen) cp_async16(smem_u32(dk), a.k + grow * a.ldk + c * 8);
+    if (r < klen) cp_async16(smem_u32(dk), a.k + grow * a.ldk + col0 + c * 8);
     else *reinterpret_cast<uint4*>(dk) = zero4;
     if (!KV_SHARED) {
       bf16* dv = sV + r * AV_PITCH + c * 8;
-      if (r < klen) cp_async16(smem_u32(dv), a.v + grow * a.ldv + c * 8);
+      if (r < klen) cp_async16(smem_u32(dv), a.v + grow * a.ldv + col0 + c * 8);
       else *reinterpret_cast<uint4*>(dv) = zero4;
     }
   }
   cp_async_wait_all();
   __syncthreads();
 
-  const int h = warp;
+  const int hl = warp & 3;            // head within the group
+  const int h = hg * 4 + hl;
   const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
-  const int ntl = LkPad >> 3;
-  for (int mt = 0; mt * 16 < a.Lq; ++mt) {
+  for (int mt = warp >> 2; mt * 16 < a.Lq; mt += 2) {
     uint32_t aq[2][4];
     {
       const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      const uint32_t base = smem_u32(sQ + row * AV_PITCH + h * 32 + (lane >> 4) * 8);
+      const uint32_t base = smem_u32(sQ + row * AV_PITCH + hl * 32 + (lane >> 4) * 8);
       ldmatrix_x4(aq[0], base);
       ldmatrix_x4(aq[1], base + 32);
     }
-    float s[AV_MAX_NT][4];
+    float s[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < AV_MAX_NT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      if (nt < ntl) {
-        uint32_t kb[4];
-        ldmatrix_x4(kb, smem_u32(sK + (nt * 8 + (lane & 7)) * AV_PITCH + h * 32 + (lane >> 3) * 8));
-        mma16816(s[nt], aq[0], kb[0], kb[1]);
-        mma16816(s[nt], aq[1], kb[2], kb[3]);
-      }
+      uint32_t kb[4];
+      ldmatrix_x4(kb, smem_u32(sK + (nt * 8 + (lane & 7)) * AV_PITCH + hl * 32 + (lane >> 3) * 8));
+      mma16816(s[nt], aq[0], kb[0], kb[1]);
+      mma16816(s[nt], aq[1], kb[2], kb[3]);
     }
+    // row max over the valid keys (tiles entirely below klen need no per-element test)
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < AV_MAX_NT; ++nt) {
-      if (nt < ntl) {
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 + 8 <= klen) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      } else if (nt * 8 < klen) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int key = nt * 8 + 2 * t + (e & 1);
-          const float v = key < klen ? s[nt][e] * sc : -INFINITY;
-          s[nt][e] = v;
-          if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+          if (key >= klen) s[nt][e] = -INFINITY;
+          if (e < 2) mx0 = fmaxf(mx0, s[nt][e]); else mx1 = fmaxf(mx1, s[nt][e]);
         }
+      } else {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
       }
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float off0 = mx0 * sc, off1 = mx1 * sc;
     float l0 = 0.f, l1 = 0.f, ts0 = 0.f, ts1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < AV_MAX_NT; ++nt) {
-      if (nt < ntl) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = nt * 8 + 2 * t + (e & 1);
-          float p = exp2f(s[nt][e] - (e < 2 ? mx0 : mx1));
-          if (e < 2) l0 += p; else l1 += p;
-          if (key < a.v_first) p = 0.f;            // dummies absorb mass but carry no value
-          else if (e < 2) ts0 += p; else ts1 += p;
-          s[nt][e] = p;
-        }
+    for (int nt = 0; nt < NT; ++nt) {
+      const float p0 = ex2_approx(fmaf(s[nt][0], sc, -off0));
+      const float p1 = ex2_approx(fmaf(s[nt][1], sc, -off0));
+      const float p2 = ex2_approx(fmaf(s[nt][2], sc, -off1));
+      const float p3 = ex2_approx(fmaf(s[nt][3], sc, -off1));
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      if (nt * 8 >= a.v_first) {            // value-carrying keys
+        ts0 += p0 + p1;
+        ts1 += p2 + p3;
+        s[nt][0] = p0; s[nt][1] = p1; s[nt][2] = p2; s[nt][3] = p3;
+      } else if (nt * 8 + 8 <= a.v_first) {  // dummies: absorb mass, carry no value
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      } else {                               // tile straddles v_first
+        const bool k0 = nt * 8 + 2 * t >= a.v_first, k1 = nt * 8 + 2 * t + 1 >= a.v_first;
+        s[nt][0] = k0 ? p0 : 0.f; s[nt][1] = k1 ? p1 : 0.f;
+        s[nt][2] = k0 ? p2 : 0.f; s[nt][3] = k1 ? p3 : 0.f;
+        ts0 += s[nt][0] + s[nt][1];
+        ts1 += s[nt][2] + s[nt][3];
       }
     }
     float o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < AV_MAX_NT / 2; ++kk) {
-      if (kk * 16 < LkPad) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        const int krow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const uint32_t vb = smem_u32(sV + krow * AV_PITCH + h * 32 + (lane >> 4) * 8);
-        uint32_t v0[4], v1[4];
-        ldmatrix_x4_trans(v0, vb);
-        ldmatrix_x4_trans(v1, vb + 32);
-        mma16816(o[0], pa, v0[0], v0[1]);
-        mma16816(o[1], pa, v0[2], v0[3]);
-        mma16816(o[2], pa, v1[0], v1[1]);
-        mma16816(o[3], pa, v1[2], v1[3]);
-      }
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const int krow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const uint32_t vb = smem_u32(sV + krow * AV_PITCH + hl * 32 + (lane >> 4) * 8);
+      uint32_t v0[4], v1[4];
+      ldmatrix_x4_trans(v0, vb);
+      ldmatrix_x4_trans(v1, vb + 32);
+      mma16816(o[0], pa, v0[0], v0[1]);
+      mma16816(o[1], pa, v0[2], v0[3]);
+      mma16816(o[2], pa, v1[0], v1[1]);
+      mma16816(o[3], pa, v1[2], v1[3]);
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    ts0 += __shfl_xor_sync(0xffffffffu, ts0, 1); ts0 += __shfl_xor_sync(0xffffffffu, ts0, 2);
-    ts1 += __shfl_xor_sync(0xffffffffu, ts1, 1); ts1 += __shfl_xor_sync(0xffffffffu, ts1, 2);
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     const int r0 = mt * 16 + g, r1 = r0 + 8;
     // the Q tile of this (m-tile, head) is dead: reuse its slots for the output
     __syncwarp();
-    bf16* d0 = sQ + r0 * AV_PITCH + h * 32 + 2 * t;
-    bf16* d1 = sQ + r1 * AV_PITCH + h * 32 + 2 * t;
+    bf16* d0 = sQ + r0 * AV_PITCH + hl * 32 + 2 * t;
+    bf16* d1 = sQ + r1 * AV_PITCH + hl * 32 + 2 * t;
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
       *reinterpret_cast<uint32_t*>(d0 + n2 * 8) = pack_bf16(o[n2][0] * i0, o[n2][1] * i0);
       *reinterpret_cast<uint32_t*>(d1 + n2 * 8) = pack_bf16(o[n2][2] * i1, o[n2][3] * i1);
     }
-    if (a.tsum && t == 0) {
-      float* ts = a.tsum + static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq;
-      if (r0 < a.Lq) ts[r0] += ts0 * i0;
-      if (r1 < a.Lq) ts[r1] += ts1 * i1;
+    if (a.tsum) {
+      ts0 += __shfl_xor_sync(0xffffffffu, ts0, 1); ts0 += __shfl_xor_sync(0xffffffffu, ts0, 2);
+      ts1 += __shfl_xor_sync(0xffffffffu, ts1, 1); ts1 += __shfl_xor_sync(0xffffffffu, ts1, 2);
+      if (t == 0) {
+        // per-layer slot: plain stores, summed by the saliency kernel (no read-modify-write chain)
+        float* ts = a.tsum + static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq;
+        if (r0 < a.Lq) ts[r0] = ts0 * i0;
+        if (r1 < a.Lq) ts[r1] = ts1 * i1;
+      }
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < a.Lq * 32; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;
-    *reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(b) * a.Lq + r) * 256 + c * 8) =
+  for (int idx = tid; idx < a.Lq * 16; idx += 256) {
+    const int r = idx >> 4, c = idx & 15;
+    *reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(b) * a.Lq + r) * 256 + col0 + c * 8) =
         *reinterpret_cast<const uint4*>(sQ + r * AV_PITCH + c * 8);
   }
+}
+
+template <int NT, bool KV_SHARED>
+static int launch_attn_video(cudaStream_t st, const AttnArgs& a, int LqPad, size_t smem) {
+  static thread_local size_t set = 0;
+  if (smem > set) {
+    FVTG_CUDA_OK(cudaFuncSetAttribute(attn_video_kernel<NT, KV_SHARED>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = smem;
+  }
+  ProfScope prof(st, PC_ATTN);
+  attn_video_kernel<NT, KV_SHARED><<<a.B * 2, 256, smem, st>>>(a, LqPad);
+  FVTG_LAUNCH_CHECK("attn_video_kernel");
+  return FVTG_OK;
 }
 
 int launch_attention(cudaStream_t st, const AttnArgs& a) {
   if (a.B <= 0) return FVTG_OK;
   {
-    const int LqPad = round_up(a.Lq, 16), LkPad = round_up(a.Lk, 16);
+    const int LqPad = round_up(a.Lq, 16);
+    const int nt = a.Lk <= 80 ? 10 : 20;
     const bool shared_kv = (a.k == a.v) && (a.ldk == a.ldv);
-    const size_t smem_v = static_cast<size_t>(LqPad + LkPad * (shared_kv ? 1 : 2)) * AV_PITCH * 2;
+    const size_t smem_v = static_cast<size_t>(LqPad + nt * 8 * (shared_kv ? 1 : 2)) * AV_PITCH * 2;
     const bool aligned = (a.ldq % 8 == 0) && (a.ldk % 8 == 0) && (a.ldv % 8 == 0) &&
                          ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) |
                            reinterpret_cast<uintptr_t>(a.v)) & 15) == 0;
-    if (LkPad <= AV_MAX_NT * 8 && smem_v <= 200 * 1024 && aligned) {
-      static thread_local size_t set_s = 0, set_d = 0;
-      ProfScope prof(st, PC_ATTN);
-      if (shared_kv) {
-        if (smem_v > set_s) {
-          FVTG_CUDA_OK(cudaFuncSetAttribute(attn_video_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-          set_s = smem_v;
-        }
-        attn_video_kernel<true><<<a.B, 256, smem_v, st>>>(a, LqPad, LkPad);
-      } else {
-        if (smem_v > set_d) {
-          FVTG_CUDA_OK(cudaFuncSetAttribute(attn_video_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-          set_d = smem_v;
-        }
-        attn_video_kernel<false><<<a.B, 256, smem_v, st>>>(a, LqPad, LkPad);
-      }
-      FVTG_LAUNCH_CHECK("attn_video_kernel");
-      return FVTG_OK;
+    if (a.Lk <= 160 && smem_v <= 200 * 1024 && aligned) {
+      if (nt == 10) return shared_kv ? launch_attn_video<10, true>(st, a, LqPad, smem_v)
+                                     : launch_attn_video<10, false>(st, a, LqPad, smem_v);
+      return shared_kv ? launch_attn_video<20, true>(st, a, LqPad, smem_v)
+                       : launch_attn_video<20, false>(st, a, LqPad, smem_v);
     }
   }
-
   const int Lkpad = round_up(a.Lk, 64);
   const size_t smem = static_cast<size_t>(Lkpad) * ATT_KS * 2 + 32 * static_cast<size_t>(Lkpad + 8) * 2;
   if (smem > 220 * 1024) return fail(FVTG_EINVAL, "attention: %d keys exceed shared memory", a.Lk);

@@ -53,7 +53,7 @@ struct AttnArgs {
   const int* klen_src;      // per-video length added to kbase: valid keys = kbase + klen_src[b]
   int kbase;
   int v_first;              // keys < v_first contribute no value (the dummy tokens, crossattention.py:385-386)
-  float* tsum;              // optional fp32 [8][B*Lq]: += sum of probabilities over keys >= v_first
+  float* tsum;              // optional fp32 [8][B*Lq] (this layer's slot): probability mass on keys >= v_first
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
 
@@ -62,7 +62,8 @@ int launch_attention(cudaStream_t st, const AttnArgs& a);
 // tile-blocked fp32 stream.
 int launch_saliency(cudaStream_t st, const float* F, const int* vlen, const float* w1,
                     const float* b1, const float* w2t, const float* b2, const float* tsum,
-                    int t2v_layers, float* sal_out, float* t2v_out, int B, int Lv);
+                    int t2v_layers, float* scratch /* B * 513 floats */, float* sal_out,
+                    float* t2v_out, int B, int Lv);
 
 // ---- decode_nms.cu -------------------------------------------------------------------------
 int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv, int n_max,

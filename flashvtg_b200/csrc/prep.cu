@@ -5,149 +5,210 @@
 
 namespace fvtg {
 
-// One warp per row.  The row is staged in shared memory (one HBM read), then mean / variance are
-// taken two-pass in fp32 exactly like torch's LayerNorm, then normalised and written as bf16.
-constexpr int LNC_WARPS = 4;
-
-template <int VEC>
-__global__ void __launch_bounds__(LNC_WARPS * 32)
+// LayerNorm over the raw feature dim + cast to bf16 (model.py:784-785 fused with operand staging).
+// TPR threads cooperate on one row and keep it in REGISTERS (one HBM read, no shared-memory
+// staging): every thread issues all of its <= 8 vector loads before the first reduction, so a
+// 256-thread CTA has 16-32 KB in flight - this kernel is the only reader of the 0.75 MB/video of
+// raw fp32 features and has to run at HBM speed.  Two-pass mean / variance like torch.
+template <int VEC, int TPR, int MAXV>
+__global__ void __launch_bounds__(256)
 ln_cast_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                const float* __restrict__ beta, bf16* __restrict__ out, int rows, int dim,
                int dim_pad) {
-  extern __shared__ float s_row[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * LNC_WARPS + warp;
-  if (row >= rows) return;
-  float* buf = s_row + static_cast<size_t>(warp) * dim_pad;
-  const float* src = in + static_cast<size_t>(row) * dim;
+  constexpr int RPB = 256 / TPR;  // rows per block
+  __shared__ float s_red[2][8];
+  const int tid = threadIdx.x;
+  const int sub = tid / TPR, tl = tid % TPR;
+  const int row = blockIdx.x * RPB + sub;
+  const bool live = row < rows;
+  const int nvec = dim / VEC;  // dim % VEC == 0 is guaranteed by the launcher
+  float x[MAXV][VEC];
+  const float* src = in + static_cast<size_t>(live ? row : 0) * dim;
   float sum = 0.f;
-  if (VEC == 2) {
-    const float2* s2 = reinterpret_cast<const float2*>(src);
-    const int n2 = dim >> 1;
-#pragma unroll 4
-    for (int i = lane; i < n2; i += 32) {
-      const float2 v = __ldg(s2 + i);
-      reinterpret_cast<float2*>(buf)[i] = v;
-      sum += v.x + v.y;
-    }
-  } else {
-    for (int i = lane; i < dim; i += 32) {
-      const float v = __ldg(src + i);
-      buf[i] = v;
-      sum += v;
-    }
-  }
-  sum = warp_sum(sum);
-  const float mean = sum / static_cast<float>(dim);
-  __syncwarp();
-  float sq = 0.f;
-  for (int i = lane; i < dim; i += 32) {
-    const float d = buf[i] - mean;
-    sq += d * d;
-  }
-  sq = warp_sum(sq);
-  const float rstd = rsqrtf(sq / static_cast<float>(dim) + 1e-5f);
-  bf16* dst = out + static_cast<size_t>(row) * dim_pad;
-  if (VEC == 2) {
-    const int n2 = dim >> 1;
-    for (int i = lane; i < (dim_pad >> 1); i += 32) {
-      float2 y = make_float2(0.f, 0.f);
-      if (i < n2) {
-        const float2 x = reinterpret_cast<const float2*>(buf)[i];
-        const float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + i);
-        const float2 b = __ldg(reinterpret_cast<const float2*>(beta) + i);
-        y.x = (x.x - mean) * rstd * g.x + b.x;
-        y.y = (x.y - mean) * rstd * g.y + b.y;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = tl + i * TPR;
+    if (live && v < nvec) {
+      if (VEC == 4) {
+        const float4 t4 = __ldcs(reinterpret_cast<const float4*>(src) + v);
+        x[i][0] = t4.x; x[i][1 % VEC] = t4.y; x[i][2 % VEC] = t4.z; x[i][3 % VEC] = t4.w;
+      } else if (VEC == 2) {
+        const float2 t2 = __ldcs(reinterpret_cast<const float2*>(src) + v);
+        x[i][0] = t2.x; x[i][1 % VEC] = t2.y;
+      } else {
+        x[i][0] = __ldcs(src + v);
       }
-      reinterpret_cast<__nv_bfloat162*>(dst)[i] = __floats2bfloat162_rn(y.x, y.y);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) x[i][e] = 0.f;
     }
-  } else {
-    for (int i = lane; i < dim_pad; i += 32) {
-      float y = 0.f;
-      if (i < dim) y = (buf[i] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
-      dst[i] = __float2bfloat16(y);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) sum += x[i][e];
+  }
+  // reduction over the TPR threads of the row (TPR is a multiple of 32)
+  auto row_sum = [&](float v, int slot) -> float {
+    v = warp_sum(v);
+    if (TPR == 32) return v;
+    const int w = tid >> 5, wpr = TPR / 32;
+    if ((tid & 31) == 0) s_red[slot][w] = v;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < wpr; ++i) tot += s_red[slot][(w / wpr) * wpr + i];
+    return tot;
+  };
+  const float mean = row_sum(sum, 0) / static_cast<float>(dim);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = tl + i * TPR;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float d = x[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(row_sum(sq, 1) / static_cast<float>(dim) + 1e-5f);
+  if (!live) return;
+  bf16* dst = out + static_cast<size_t>(row) * dim_pad;
+  const int nvec_pad = dim_pad / VEC;
+#pragma unroll
+  for (int i = 0; i < MAXV + 1; ++i) {
+    const int v = tl + i * TPR;
+    if (v >= nvec_pad) break;
+    float y[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) y[e] = 0.f;
+    if (i < MAXV && v < nvec) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        y[e] = (x[i < MAXV ? i : 0][e] - mean) * rstd * __ldg(gamma + v * VEC + e) + __ldg(beta + v * VEC + e);
+    }
+    if (VEC == 4) {
+      uint2 u;
+      u.x = pack_bf16(y[0], y[1 % VEC]);
+      u.y = pack_bf16(y[2 % VEC], y[3 % VEC]);
+      *reinterpret_cast<uint2*>(dst + v * 4) = u;
+    } else if (VEC == 2) {
+      *reinterpret_cast<uint32_t*>(dst + v * 2) = pack_bf16(y[0], y[1 % VEC]);
+    } else {
+      dst[v] = __float2bfloat16(y[0]);
     }
   }
 }
 
-int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const float* beta,
-                   bf16* out, int rows, int dim, int dim_pad) {
-  if (rows <= 0) return FVTG_OK;
-  const size_t smem = static_cast<size_t>(LNC_WARPS) * dim_pad * sizeof(float);
-  if (smem > 200 * 1024) return fail(FVTG_EINVAL, "ln_cast: feature dim %d too large", dim);
-  const int grid = (rows + LNC_WARPS - 1) / LNC_WARPS;
+template <int VEC>
+static int launch_ln_cast_v(cudaStream_t st, const float* in, const float* gamma, const float* beta,
+                            bf16* out, int rows, int dim, int dim_pad) {
+  const int nvec_pad = dim_pad / VEC;
+  // smallest TPR whose 8 vectors per thread cover the padded row; rows wider than 256 x 8 vectors
+  // (Charades-VGG: 4098 floats) take the 18-vector variant
+  int tpr = 32;
+  while (tpr < 256 && tpr * 8 < nvec_pad) tpr *= 2;
+  const bool wide = tpr * 8 < nvec_pad;
+  if (wide && tpr * 18 < nvec_pad) return fail(FVTG_EINVAL, "ln_cast: feature dim %d too large", dim);
+  const int rpb = 256 / tpr;
+  const int grid = (rows + rpb - 1) / rpb;
   ProfScope prof(st, PC_LNCAST);
-  const bool vec2 = (dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7) == 0) &&
-                    ((reinterpret_cast<uintptr_t>(gamma) & 7) == 0) &&
-                    ((reinterpret_cast<uintptr_t>(beta) & 7) == 0);
-  if (vec2) {
-    static thread_local size_t set2 = 0;
-    if (smem > set2) {
-      FVTG_CUDA_OK(cudaFuncSetAttribute(ln_cast_kernel<2>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set2 = smem;
-    }
-    ln_cast_kernel<2><<<grid, LNC_WARPS * 32, smem, st>>>(in, gamma, beta, out, rows, dim, dim_pad);
+  if (wide) {
+    ln_cast_kernel<VEC, 256, 18><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad);
   } else {
-    static thread_local size_t set1 = 0;
-    if (smem > set1) {
-      FVTG_CUDA_OK(cudaFuncSetAttribute(ln_cast_kernel<1>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set1 = smem;
+    switch (tpr) {
+      case 32: ln_cast_kernel<VEC, 32, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
+      case 64: ln_cast_kernel<VEC, 64, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
+      case 128: ln_cast_kernel<VEC, 128, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
+      default: ln_cast_kernel<VEC, 256, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
     }
-    ln_cast_kernel<1><<<grid, LNC_WARPS * 32, smem, st>>>(in, gamma, beta, out, rows, dim, dim_pad);
   }
   FVTG_LAUNCH_CHECK("ln_cast_kernel");
   return FVTG_OK;
 }
 
+int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const float* beta,
+                   bf16* out, int rows, int dim, int dim_pad) {
+  if (rows <= 0) return FVTG_OK;
+  const uintptr_t ai = reinterpret_cast<uintptr_t>(in);
+  if (dim % 4 == 0 && dim_pad % 4 == 0 && (ai & 15) == 0)
+    return launch_ln_cast_v<4>(st, in, gamma, beta, out, rows, dim, dim_pad);
+  if (dim % 2 == 0 && dim_pad % 2 == 0 && (ai & 7) == 0)
+    return launch_ln_cast_v<2>(st, in, gamma, beta, out, rows, dim, dim_pad);
+  return launch_ln_cast_v<1>(st, in, gamma, beta, out, rows, dim, dim_pad);
+}
+
 // pos[b*Lv + i][c]: e = (i+1) / (len + 1e-6) * 2pi ; even c: sin(e / w_c), odd c: cos(e / w_c),
 // w_c = 10000^(2*floor(c/2)/256).
 __global__ void posenc_kernel(float* __restrict__ pos, const int* __restrict__ vlen, int B, int Lv) {
-  const int row = blockIdx.x;
-  const int c = threadIdx.x;
-  const int b = row / Lv, i = row - b * Lv;
-  const int len = vlen[b];
-  float v = 0.f;
-  if (i < len) {
-    const float e = static_cast<float>(i + 1) / (static_cast<float>(len) + 1e-6f) * 6.283185307179586f;
-    const float w = powf(10000.f, static_cast<float>(2 * (c >> 1)) / 256.f);
-    const float a = e / w;
-    v = (c & 1) ? cosf(a) : sinf(a);
+  const long long tt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // lanes run over consecutive rows of one 4-column group: 16-byte stores contiguous in the
+  // tile-blocked layout
+  const long long rows = static_cast<long long>(B) * Lv;
+  const long long rows_pad = (rows + 127) & ~127ll;
+  if (tt >= rows_pad * 64) return;
+  const long long tile = tt / (64 * 128);
+  const int rem = static_cast<int>(tt - tile * (64 * 128));
+  const int c4 = rem >> 7, rin = rem & 127;
+  const long long row = tile * 128 + rin;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < rows) {
+    const int b = static_cast<int>(row / Lv), i = static_cast<int>(row - static_cast<long long>(b) * Lv);
+    const int len = vlen[b];
+    if (i < len) {
+      const float e = static_cast<float>(i + 1) / (static_cast<float>(len) + 1e-6f) * 6.283185307179586f;
+      const float w0 = powf(10000.f, static_cast<float>(4 * c4) / 256.f);       // columns 4c4, 4c4+1
+      const float w1 = powf(10000.f, static_cast<float>(4 * c4 + 2) / 256.f);   // columns 4c4+2, +3
+      const float a0 = e / w0, a1 = e / w1;
+      v = make_float4(sinf(a0), cosf(a0), sinf(a1), cosf(a1));
+    }
   }
-  pos[blk_off(row, c)] = v;
+  *reinterpret_cast<float4*>(pos + (tile * 64 + c4) * 512 + rin * 4) = v;
 }
 
 int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv) {
   if (B * Lv <= 0) return FVTG_OK;
+  const long long rows_pad = ((static_cast<long long>(B) * Lv + 127) / 128) * 128;
+  const long long threads = rows_pad * 64;
   ProfScope prof(st, PC_OTHER);
-  posenc_kernel<<<B * Lv, 256, 0, st>>>(pos, vlen, B, Lv);
+  posenc_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(pos, vlen, B, Lv);
   FVTG_LAUNCH_CHECK("posenc_kernel");
   return FVTG_OK;
 }
 
+// thread = (video, dummy row, 4 columns)
 __global__ void fill_dummy_kernel(const float* __restrict__ dtok, const float* __restrict__ dpos,
                                   float* __restrict__ X, bf16* __restrict__ Xb,
                                   bf16* __restrict__ XPb, float* __restrict__ pos_d, int B, int S,
                                   int nd) {
-  const int c = threadIdx.x;
-  const int j = blockIdx.x;  // 0..S-1
-  if (blockIdx.y == 0) pos_d[j * 256 + c] = j < nd ? dpos[j * 256 + c] : 0.f;
-  if (j >= nd) return;
-  const float t = dtok[j * 256 + c], p = dpos[j * 256 + c];
-  for (int b = blockIdx.y; b < B; b += gridDim.y) {
-    const size_t o = (static_cast<size_t>(b) * S + j) * 256 + c;
-    X[blk_off(static_cast<size_t>(b) * S + j, c)] = t;
-    Xb[o] = __float2bfloat16(t);
-    XPb[o] = __float2bfloat16(t + p);
+  const long long tt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tt < static_cast<long long>(S) * 64) {  // the [dummy_pos ‖ 0] table
+    const int j = static_cast<int>(tt >> 6), c = static_cast<int>(tt & 63) * 4;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < nd) p = *reinterpret_cast<const float4*>(dpos + j * 256 + c);
+    *reinterpret_cast<float4*>(pos_d + j * 256 + c) = p;
   }
+  if (tt >= static_cast<long long>(B) * nd * 64) return;
+  const int c = static_cast<int>(tt & 63) * 4;
+  const long long rj = tt >> 6;
+  const int b = static_cast<int>(rj / nd), j = static_cast<int>(rj - static_cast<long long>(b) * nd);
+  const float4 tk = *reinterpret_cast<const float4*>(dtok + j * 256 + c);
+  const float4 p = *reinterpret_cast<const float4*>(dpos + j * 256 + c);
+  const size_t row = static_cast<size_t>(b) * S + j;
+  *reinterpret_cast<float4*>(X + blk_off(row, c)) = tk;
+  uint2 u, up;
+  u.x = pack_bf16(tk.x, tk.y); u.y = pack_bf16(tk.z, tk.w);
+  up.x = pack_bf16(tk.x + p.x, tk.y + p.y); up.y = pack_bf16(tk.z + p.z, tk.w + p.w);
+  *reinterpret_cast<uint2*>(Xb + row * 256 + c) = u;
+  *reinterpret_cast<uint2*>(XPb + row * 256 + c) = up;
 }
 
 int launch_fill_dummy(cudaStream_t st, const float* dtok, const float* dpos, float* X, bf16* Xb,
                       bf16* XPb, float* pos_d, int B, int S, int nd) {
-  dim3 grid(S, B < 64 ? B : 64);
+  long long threads = static_cast<long long>(B) * nd * 64;
+  if (threads < static_cast<long long>(S) * 64) threads = static_cast<long long>(S) * 64;
   ProfScope prof(st, PC_OTHER);
-  fill_dummy_kernel<<<grid, 256, 0, st>>>(dtok, dpos, X, Xb, XPb, pos_d, B, S, nd);
+  fill_dummy_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(dtok, dpos, X, Xb, XPb,
+                                                                           pos_d, B, S, nd);
   FVTG_LAUNCH_CHECK("fill_dummy_kernel");
   return FVTG_OK;
 }
