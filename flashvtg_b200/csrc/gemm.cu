@@ -74,18 +74,6 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
   return v;
 }
 
-__device__ __forceinline__ void store_bf16x32(bf16* dst, const float* y) {
-  uint4* p = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(y[q * 8 + 0], y[q * 8 + 1]);
-    u.y = pack_bf16(y[q * 8 + 2], y[q * 8 + 3]);
-    u.z = pack_bf16(y[q * 8 + 4], y[q * 8 + 5]);
-    u.w = pack_bf16(y[q * 8 + 6], y[q * 8 + 7]);
-    p[q] = u;
-  }
-}
 // 32 consecutive columns of one row, starting at column c0: row-major (stride 4 floats between the
 // 16-byte groups) or tile-blocked (stride 512 floats).
 __device__ __forceinline__ void store_f32x32(float* base, size_t row, int c0, bool blocked,
@@ -109,22 +97,27 @@ __device__ __forceinline__ void add_f32x32(const float* base, size_t row, int c0
   }
 }
 
+__device__ __forceinline__ void gemm_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmArgs g) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+            const __grid_constant__ GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint8_t* stage_out = smem + GEMM_STAGES * GEMM_STAGE_BYTES;  // 4 swizzled [128][64] bf16 units
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + GEMM_OUT_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + GEMM_STAGES;
   uint64_t* tfull = bars + 2 * GEMM_STAGES;
   uint64_t* tempty = bars + 2 * GEMM_STAGES + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
-  float* s_bias = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + 256);
+  float* s_bias = reinterpret_cast<float*>(stage_out + GEMM_OUT_BYTES + 256);
   float* s_gamma = s_bias + 1024;
   float* s_beta = s_gamma + 256;
   float* s_dotw = s_beta + 256;
+  float2* s_stat = reinterpret_cast<float2*>(s_dotw + 256);  // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) {
@@ -146,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_mbar_init();
   }
@@ -157,15 +151,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp >= 4) {
     const GemmEpi& e = g.epi;
     const int t = threadIdx.x - 128;
-    for (int i = t; i < g.N && i < 1024; i += 128) s_bias[i] = e.bias ? e.bias[i] : 0.f;
+    for (int i = t; i < g.N && i < 1024; i += 256) s_bias[i] = e.bias ? e.bias[i] : 0.f;
     if (e.mode == EPI_ROW && e.gamma) {
-      for (int i = t; i < 256; i += 128) {
+      for (int i = t; i < 256; i += 256) {
         s_gamma[i] = e.gamma[i];
         s_beta[i] = e.beta[i];
       }
     }
     if (e.mode == EPI_DOT)
-      for (int i = t; i < 128; i += 128) s_dotw[i] = e.dotw[i];
+      for (int i = t; i < 128; i += 256) s_dotw[i] = e.dotw[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -225,16 +219,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ----------------------------------------------------------- epilogue --
+    // 8 warps, two threads per accumulator row: TMEM lane quadrant = warp % 4, column half = hf.
     const GemmEpi& e = g.epi;
-    const int wq = warp - 4;  // TMEM lane quadrant this warp may access
+    const int ew = warp - 4;
+    const int wq = ew & 3, hf = ew >> 2;
+    const int r = wq * 32 + lane;
+    const int HC = BN >> 1;  // columns owned by this thread
+    const bool leader = threadIdx.x == 128;
+    // bf16 tile outputs with an identity row map leave through shared memory + TMA (coalesced)
+    const bool staged = (e.mode == EPI_TILE) ||
+                        (e.mode == EPI_ROW && e.out_bf16 && (e.rowmap == RM_NONE || e.rowmap == RM_CHAIN));
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
-      const int row = mt * GEMM_BM + wq * 32 + lane;
+      const int row = mt * GEMM_BM + r;
       const int n0 = nt * BN;
       const RowInfo ri = map_row(g, row);
+      if (staged && it > 0) {  // the previous tile's TMA store must be done reading the staging tile
+        if (leader) tma_store_wait_read();
+        gemm_epi_bar();
+      }
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + acc * 256 + (static_cast<uint32_t>(wq * 32) << 16);
@@ -243,12 +249,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       if (e.mode == EPI_ROW) {
         const bool ln = e.gamma != nullptr;
-        float mean = 0.f, rstd = 1.f;
         const bool has_res = e.res && ri.inb;
         const bool blk = e.f32_blocked != 0;
+        float mean = 0.f, rstd = 1.f;
         if (ln) {
           float s1 = 0.f, s2 = 0.f, shift = 0.f;
-          for (int c0 = 0; c0 < 256; c0 += 32) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const int c0 = hf * 128 + c * 32;
             tmem_ld32(tacc + c0, u);
             tmem_ld_wait();
 #pragma unroll
@@ -256,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (has_res) add_f32x32(e.res, row, c0, blk, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, e.prelu);
-            if (c0 == 0) shift = v[0];
+            if (c == 0) shift = v[0];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float d = v[j] - shift;
@@ -269,15 +277,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tmem_st32(tacc + c0, u);
           }
           tmem_st_wait();
-          const float m1 = s1 * (1.f / 256.f);
-          const float var = fmaxf(s2 * (1.f / 256.f) - m1 * m1, 0.f);
-          mean = shift + m1;
+          s_stat[hf * 128 + r] = make_float2(shift + s1 * (1.f / 128.f), s2 - s1 * s1 * (1.f / 128.f));
+          gemm_epi_bar();
+          const float2 a = s_stat[r], b2 = s_stat[128 + r];
+          const float dm = a.x - b2.x;
+          mean = 0.5f * (a.x + b2.x);
+          const float var = fmaxf((a.y + b2.y + dm * dm * 64.f) * (1.f / 256.f), 0.f);
           rstd = rsqrtf(var + 1e-5f);
         }
         int prow = row;
         if (e.pos_mod > 0) prow = row % e.pos_mod;
         const bool st_pos = e.out_bf16_pos && ri.inb && (e.pos_rowlim <= 0 || prow < e.pos_rowlim);
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = hf * 128 + c * 32;
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
           if (ln) {
@@ -299,24 +312,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
+          if (staged) st_shared_bf16x32(stage_out + (c0 >> 6) * GEMM_A_BYTES, r, (c0 & 63) >> 3, v);
           if (ri.inb) {
             const size_t o = static_cast<size_t>(ri.dst) * 256 + c0;
             if (e.out_f32 && !(ln && e.f32_preln)) store_f32x32(e.out_f32, ri.dst, c0, blk, v);
-            if (e.out_bf16) store_bf16x32(e.out_bf16 + o, v);
+            if (e.out_bf16 && !staged) st_global_bf16x32(e.out_bf16 + o, v);
             if (e.rowmap == RM_TXT) {
-              if (e.out_x1) store_bf16x32(e.out_x1 + static_cast<size_t>(ri.x1) * 256 + c0, v);
+              if (e.out_x1) st_global_bf16x32(e.out_x1 + static_cast<size_t>(ri.x1) * 256 + c0, v);
             } else if (e.rowmap == RM_CHAIN && e.rm_c && ri.valid) {
-              if (e.out_x1) store_bf16x32(e.out_x1 + static_cast<size_t>(ri.x1) * 256 + c0, v);
-              if (e.out_x2) store_bf16x32(e.out_x2 + static_cast<size_t>(ri.x2) * 256 + c0, v);
+              if (e.out_x1) st_global_bf16x32(e.out_x1 + static_cast<size_t>(ri.x1) * 256 + c0, v);
+              if (e.out_x2) st_global_bf16x32(e.out_x2 + static_cast<size_t>(ri.x2) * 256 + c0, v);
             }
             if (st_pos) {
               if (e.pos) add_f32x32(e.pos, prow, c0, blk && e.pos_mod <= 0, v);
-              store_bf16x32(e.out_bf16_pos + o, v);
+              st_global_bf16x32(e.out_bf16_pos + o, v);
             }
           }
         }
       } else if (e.mode == EPI_TILE) {
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = hf * HC; c0 < (hf + 1) * HC; c0 += 32) {
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
 #pragma unroll
@@ -324,32 +338,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float x = apply_act(__uint_as_float(u[j]) + s_bias[n0 + c0 + j], e.act, e.prelu);
             v[j] = ri.valid ? x : 0.f;
           }
-          if (ri.inb) store_bf16x32(e.out + static_cast<size_t>(ri.dst) * e.ld_out + n0 + c0, v);
+          st_shared_bf16x32(stage_out + (c0 >> 6) * GEMM_A_BYTES, r, (c0 & 63) >> 3, v);
         }
       } else if (e.mode == EPI_DOT) {
         float dot = 0.f;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             dot += fmaxf(__uint_as_float(u[j]) + s_bias[c0 + j], 0.f) * s_dotw[c0 + j];
         }
-        if (ri.valid) e.out_dot[static_cast<size_t>(ri.b) * e.geo.n_max + ri.n] = dot + e.dotb;
+        if (hf == 1) s_stat[r].x = dot;
+        gemm_epi_bar();
+        if (hf == 0 && ri.valid)
+          e.out_dot[static_cast<size_t>(ri.b) * e.geo.n_max + ri.n] = dot + s_stat[r].x + e.dotb;
+        gemm_epi_bar();  // s_stat is rewritten by the next tile
       } else {  // EPI_COORD
-        tmem_ld16(tacc, u);
-        tmem_ld_wait();
-        if (ri.valid) {
-          const float c = e.coef[ri.lvl];
-          float* o = e.out_coord + (static_cast<size_t>(ri.b) * e.geo.n_max + ri.n) * 2;
-          o[0] = expf(__uint_as_float(u[0]) + s_bias[0]) * c;
-          o[1] = expf(__uint_as_float(u[1]) + s_bias[1]) * c;
+        if (hf == 0) {
+          tmem_ld16(tacc, u);
+          tmem_ld_wait();
+          if (ri.valid) {
+            const float c = e.coef[ri.lvl];
+            float* o = e.out_coord + (static_cast<size_t>(ri.b) * e.geo.n_max + ri.n) * 2;
+            o[0] = expf(__uint_as_float(u[0]) + s_bias[0]) * c;
+            o[1] = expf(__uint_as_float(u[1]) + s_bias[1]) * c;
+          }
         }
       }
       tc_fence_before();
+      if (staged) {
+        fence_proxy_async_smem();
+        gemm_epi_bar();
+        if (leader) {
+          const int units = (e.mode == EPI_ROW ? 256 : BN) >> 6;
+          for (int kb = 0; kb < units; ++kb)
+            tma_store_2d(&tmOut, stage_out + kb * GEMM_A_BYTES, n0 + kb * 64, mt * GEMM_BM);
+          tma_store_commit();
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (staged && leader) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -380,16 +411,27 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
                                       GEMM_SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap ta, ta2, tb;
+  CUtensorMap ta, ta2, tb, to;
   FVTG_TRY(make_tmap_bf16(&ta, a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
   FVTG_TRY(make_tmap_bf16(&ta2, a2 ? a2 : a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
   const uint64_t ktot = static_cast<uint64_t>(args.ntaps) * args.kb_per_tap * GEMM_BK;
   FVTG_TRY(make_tmap_bf16(&tb, w, args.N, ktot, ktot, args.BN, GEMM_BK));
+  {  // bf16 tile output leaving through the staging tile + TMA store (rows >= M are clipped)
+    const GemmEpi& e = args.epi;
+    const void* optr = w;
+    uint64_t ocols = ktot, opitch = ktot, orows = args.N;
+    if (e.mode == EPI_TILE) {
+      optr = e.out; ocols = e.ld_out; opitch = e.ld_out; orows = args.M;
+    } else if (e.mode == EPI_ROW && e.out_bf16 && (e.rowmap == RM_NONE || e.rowmap == RM_CHAIN)) {
+      optr = e.out_bf16; ocols = 256; opitch = 256; orows = args.M;
+    }
+    FVTG_TRY(make_tmap_bf16(&to, optr, orows, ocols, opitch, GEMM_BM, GEMM_BK));
+  }
   const int m_tiles = (args.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = m_tiles * (args.N / args.BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(st, PC_GEMM);
-  gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, ta2, tb, args);
+  gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, ta2, tb, to, args);
   FVTG_LAUNCH_CHECK("gemm_kernel");
   return FVTG_OK;
 }

@@ -2,11 +2,12 @@
 // tcgen05 GEMM  C[M][N] = A[M][K] * W[N][K]^T  (bf16 in, fp32 accumulate in TMEM)
 // with the row-wise work of the reference fused into its epilogue.
 //
-//   warp 0      TMA producer   (A / W tiles -> 4-stage SWIZZLE_128B smem ring)
+//   warp 0      TMA producer   (A / W tiles -> 3-stage SWIZZLE_128B smem ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, 128 x BN x 16)
 //   warp 2      TMEM allocator (512 columns = two BN<=256 accumulators, double buffered)
-//   warps 4..7  epilogue       (tcgen05.ld -> bias / activation / residual / LayerNorm /
-//                               row-dot / exp -> global), overlapping the next tile's MMAs
+//   warps 4..11 epilogue       (two threads per row; tcgen05.ld -> bias / activation / residual /
+//                               LayerNorm / row-dot / exp; bf16 tiles leave through a swizzled
+//                               staging tile + TMA store), overlapping the next tile's MMAs
 //
 // "Taps": K is a sequence of ntaps slabs; slab t reads A rows shifted by tap_shift[t]
 // (TMA zero-fills out-of-range rows).  That turns the reference's Conv2d(1,k) /
@@ -21,15 +22,17 @@ namespace fvtg {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_MAX_TAPS = 8;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB
 constexpr int GEMM_B_BYTES_MAX = 256 * GEMM_BK * 2;        // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES_MAX;
+constexpr int GEMM_OUT_BYTES = 4 * GEMM_A_BYTES;           // staging tile for TMA stores: 128 x 256 bf16
 constexpr int GEMM_PARAM_FLOATS = 1024 + 256 + 256 + 256;  // bias, gamma, beta, dotw
-constexpr int GEMM_SMEM_BYTES =
-    GEMM_STAGES * GEMM_STAGE_BYTES + 256 + GEMM_PARAM_FLOATS * 4 + 1024 /*align slack*/;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_OUT_BYTES + 256 +
+                                GEMM_PARAM_FLOATS * 4 + 2 * 128 * 8 /*LN stats*/ + 1024 /*align slack*/;
+static_assert(GEMM_SMEM_BYTES <= 232448, "gemm kernel shared memory over the 227 KB limit");
 
 enum EpiMode { EPI_ROW = 0, EPI_TILE = 1, EPI_DOT = 2, EPI_COORD = 3 };
 enum RowMap { RM_NONE = 0, RM_TXT = 1, RM_CHAIN = 2, RM_H1 = 3, RM_H2 = 4 };

@@ -47,36 +47,6 @@ static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// byte offset of 16-byte chunk c (0..7) of row r inside one SWIZZLE_128B unit
-__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-  return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
-}
-
-__device__ __forceinline__ void st_shared_bf16x32(uint8_t* unit, int r, int c_first, const float* y) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(y[q * 8 + 0], y[q * 8 + 1]);
-    u.y = pack_bf16(y[q * 8 + 2], y[q * 8 + 3]);
-    u.z = pack_bf16(y[q * 8 + 4], y[q * 8 + 5]);
-    u.w = pack_bf16(y[q * 8 + 6], y[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(unit + sw128_off(r, c_first + q)) = u;
-  }
-}
-
-__device__ __forceinline__ void st_global_bf16x32(bf16* dst, const float* y) {
-  uint4* p = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(y[q * 8 + 0], y[q * 8 + 1]);
-    u.y = pack_bf16(y[q * 8 + 2], y[q * 8 + 3]);
-    u.z = pack_bf16(y[q * 8 + 4], y[q * 8 + 5]);
-    u.w = pack_bf16(y[q * 8 + 6], y[q * 8 + 7]);
-    p[q] = u;
-  }
-}
-
 __global__ void __launch_bounds__(LK_THREADS, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWo,
              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,

@@ -214,3 +214,50 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 }  // namespace fvtg
+
+namespace fvtg {
+// ------------------------------------------------------------- TMA stores --
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside one [rows][64 bf16] SWIZZLE_128B unit
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
+}
+// 32 consecutive bf16 columns (4 chunks starting at chunk c_first) of row r into a swizzled unit
+__device__ __forceinline__ void st_shared_bf16x32(uint8_t* unit, int r, int c_first, const float* y) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(y[q * 8 + 0], y[q * 8 + 1]);
+    u.y = pack_bf16(y[q * 8 + 2], y[q * 8 + 3]);
+    u.z = pack_bf16(y[q * 8 + 4], y[q * 8 + 5]);
+    u.w = pack_bf16(y[q * 8 + 6], y[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(unit + sw128_off(r, c_first + q)) = u;
+  }
+}
+__device__ __forceinline__ void st_global_bf16x32(__nv_bfloat16* dst, const float* y) {
+  uint4* p = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(y[q * 8 + 0], y[q * 8 + 1]);
+    u.y = pack_bf16(y[q * 8 + 2], y[q * 8 + 3]);
+    u.z = pack_bf16(y[q * 8 + 4], y[q * 8 + 5]);
+    u.w = pack_bf16(y[q * 8 + 6], y[q * 8 + 7]);
+    p[q] = u;
+  }
+}
+}  // namespace fvtg
