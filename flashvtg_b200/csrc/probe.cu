@@ -1,36 +1,63 @@
-// Debug probe (not on the product path): how fast can every SM stream the SAME weight matrix
-// from L2 through TMA into a shared-memory ring of `stages` 16 KB units, with no consumer work?
-// Answers whether the fused layer kernel's weight ring is latency- or bandwidth-limited.
+// Debug probes (not on the product path), run by tools/probe_tma.py on a B200:
+//  * fvtg_dbg_tma_probe: how fast can every SM stream the SAME weight matrix from L2 into a
+//    shared-memory ring of `stages` units with no consumer work?  mode 0: 2-D tensor boxes
+//    {64 cols, 128 rows} (16 KB, SWIZZLE_128B) ; mode 1: 1-D bulk copies of contiguous 16 KB
+//    (weights pre-packed as shared-memory images) ; mode 2: 2-D boxes {64, 256} (32 KB) ;
+//    mode 3: mode 0 issued from two producer threads.
+//  * fvtg_dbg_mma_probe: cycles per tcgen05.mma (128 x N x 16, bf16, both operands in shared
+//    memory) issued back to back on resident tiles: the tensor-pipe floor for N = 128 / 256.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace fvtg {
 
-__global__ void __launch_bounds__(64, 1)
-tma_stream_probe_kernel(const __grid_constant__ CUtensorMap tmW, int stages, int units, int rows_total,
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes),
+        "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1)
+tma_stream_probe_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2,
+                        const uint8_t* wraw, int mode, int stages, int units, int rows_total,
                         long long* out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + 13 * 16384);
   uint64_t* empty = full + 16;
+  const int ub = (mode == 2) ? 32768 : 16384;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     fence_mbar_init();
     prefetch_tmap(&tmW);
+    prefetch_tmap(&tmW2);
   }
   __syncthreads();
   const long long t0 = clock64();
-  if (threadIdx.x == 0) {  // producer
-    int s = 0; uint32_t ph = 0;
-    for (int u = 0; u < units; ++u) {
+  const int nprod = (mode == 3) ? 2 : 1;
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < nprod) {  // producer(s): warp 0 (and warp 1 in mode 3)
+    for (int u = w; u < units; u += nprod) {
+      const int s = u % stages;
+      const uint32_t ph = (u / stages) & 1;
       mbar_wait(&empty[s], ph ^ 1);
-      mbar_expect_tx(&full[s], 16384);
-      const int r0 = (u * 128) % rows_total;
-      tma_load_2d(smem + s * 16384, &tmW, ((u / (rows_total / 128)) % 4) * 64, r0, &full[s]);
-      if (++s == stages) { s = 0; ph ^= 1; }
+      mbar_expect_tx(&full[s], ub);
+      if (mode == 1) {
+        bulk_load_1d(smem + s * ub, wraw + static_cast<size_t>(u % (rows_total * 512 / 16384)) * 16384,
+                     16384, &full[s]);
+      } else if (mode == 2) {
+        const int r0 = (u * 256) % rows_total;
+        tma_load_2d(smem + s * ub, &tmW2, ((u / (rows_total / 256)) % 4) * 64, r0, &full[s]);
+      } else {
+        const int r0 = (u * 128) % rows_total;
+        tma_load_2d(smem + s * ub, &tmW, ((u / (rows_total / 128)) % 4) * 64, r0, &full[s]);
+      }
     }
-  } else if (threadIdx.x == 32) {  // consumer: release immediately
+  } else if (threadIdx.x == 64) {  // consumer: release immediately
     int s = 0; uint32_t ph = 0;
     for (int u = 0; u < units; ++u) {
       mbar_wait(&full[s], ph);
@@ -42,19 +69,195 @@ tma_stream_probe_kernel(const __grid_constant__ CUtensorMap tmW, int stages, int
   if (threadIdx.x == 0) out_cycles[blockIdx.x] = clock64() - t0;
 }
 
+// One thread issues `iters` MMAs (each a full K = 64 unit: 4 x tcgen05.mma 128 x N x 16) on tiles
+// resident in shared memory, commits, waits.  out[0] = cycles.
+__global__ void __launch_bounds__(128, 1)
+mma_rate_probe_kernel(int N, int iters, int nbuf, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t holder;
+  for (int i = threadIdx.x; i < 12 * 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(&holder, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = holder;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint32_t base = smem_u32(smem);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int b = i % nbuf;
+      const uint64_t da = umma_desc_sw128(base + b * 16384);
+      const uint64_t db = umma_desc_sw128(base + 4 * 16384 + (b % 2) * 32768);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + (i & 1) * 256, da + 2 * k, db + 2 * k, idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    out_cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+
+// ---- v3: weight streaming with an honest producer loop (no integer divisions), optional
+// cluster multicast.  Every CTA of a cluster of `csize` loads rows [rank*128/csize, ...) of each
+// 16 KB unit and multicasts the slice to all CTAs; nprod producer lanes (different warps) split
+// the unit stream.  Consumer releases each stage to every CTA of the cluster.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, int c0, int c1,
+                                               uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+tma_stream_probe3_kernel(const __grid_constant__ CUtensorMap tmW, int csize, int nprod, int stages,
+                         int passes, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 12 * 16384);
+  uint64_t* empty = full + 16;
+  const uint32_t rank = csize > 1 ? cluster_ctarank() : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], nprod > 1 ? 1 : 1); mbar_init(&empty[s], csize); }
+    fence_mbar_init();
+    prefetch_tmap(&tmW);
+  }
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  const long long t0 = clock64();
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int slice_rows = 128 / csize;
+  const uint32_t slice_bytes = 16384 / csize;
+  const uint16_t mask = static_cast<uint16_t>((1u << csize) - 1);
+  // unit stream per pass: 18 row blocks x 4 k blocks of the [2304][256] matrix
+  if (lane == 0 && w < nprod) {
+    // producer w handles stages s with s % nprod == w (stages % nprod == 0 required)
+    uint32_t ph = 0;
+    int s = 0, sp = 0;  // stage, stage % nprod (kept as counters: no division in the timed loop)
+    for (int p = 0; p < passes; ++p)
+      for (int rb = 0; rb < 18; ++rb)
+        for (int kb = 0; kb < 4; ++kb) {
+          if (sp == w) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], 16384);
+            if (csize > 1)
+              tma_load_2d_mc(smem + s * 16384 + rank * slice_bytes, &tmW, kb * 64,
+                             rb * 128 + rank * slice_rows, &full[s], mask);
+            else
+              tma_load_2d(smem + s * 16384, &tmW, kb * 64, rb * 128, &full[s]);
+          }
+          if (++sp == nprod) sp = 0;
+          if (++s == stages) { s = 0; sp = 0; ph ^= 1; }
+        }
+  } else if (threadIdx.x == 160) {  // consumer: release immediately to every CTA of the cluster
+    int s = 0; uint32_t ph = 0;
+    const int units = passes * 72;
+    for (int u = 0; u < units; ++u) {
+      mbar_wait(&full[s], ph);
+      if (csize > 1) {
+        for (int c = 0; c < csize; ++c) mbar_arrive_remote(&empty[s], c);
+      } else {
+        mbar_arrive(&empty[s]);
+      }
+      if (++s == stages) { s = 0; ph ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  if (threadIdx.x == 0) out_cycles[blockIdx.x] = clock64() - t0;
+}
+
 }  // namespace fvtg
 
 extern "C" int32_t fvtg_dbg_tma_probe(const void* w_bf16 /* [rows][256] */, int32_t rows, int32_t stages,
-                                      int32_t units, int32_t grid, void* out_cycles, void* stream) {
+                                      int32_t units, int32_t grid, int32_t mode, void* out_cycles,
+                                      void* stream) {
   using namespace fvtg;
-  if (stages < 1 || stages > 13 || rows % 128) return fail(FVTG_EINVAL, "probe: bad arguments");
-  CUtensorMap tw;
+  const int ub = mode == 2 ? 32768 : 16384;
+  if (stages < 1 || stages * ub > 13 * 16384 || rows % 256) return fail(FVTG_EINVAL, "probe: bad arguments");
+  CUtensorMap tw, tw2;
   FVTG_TRY(make_tmap_bf16(&tw, w_bf16, rows, 256, 256, 128, 64));
+  FVTG_TRY(make_tmap_bf16(&tw2, w_bf16, rows, 256, 256, 256, 64));
   const int smem = 13 * 16384 + 512 + 1024;
   FVTG_CUDA_OK(cudaFuncSetAttribute(tma_stream_probe_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tma_stream_probe_kernel<<<grid, 64, smem, static_cast<cudaStream_t>(stream)>>>(
-      tw, stages, units, rows, static_cast<long long*>(out_cycles));
+  tma_stream_probe_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      tw, tw2, static_cast<const uint8_t*>(w_bf16), mode, stages, units, rows,
+      static_cast<long long*>(out_cycles));
   FVTG_LAUNCH_CHECK("tma_stream_probe_kernel");
+  return FVTG_OK;
+}
+
+extern "C" int32_t fvtg_dbg_mma_probe(int32_t N, int32_t iters, int32_t nbuf, int32_t grid,
+                                      void* out_cycles, void* stream) {
+  using namespace fvtg;
+  if ((N != 128 && N != 256 && N != 64) || nbuf < 1 || nbuf > 4) return fail(FVTG_EINVAL, "mma probe: bad arguments");
+  const int smem = 12 * 16384 + 1024;
+  FVTG_CUDA_OK(cudaFuncSetAttribute(mma_rate_probe_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_probe_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      N, iters, nbuf, static_cast<long long*>(out_cycles));
+  FVTG_LAUNCH_CHECK("mma_rate_probe_kernel");
+  return FVTG_OK;
+}
+
+extern "C" int32_t fvtg_dbg_tma_probe3(const void* w_bf16 /* [2304][256] */, int32_t csize, int32_t nprod,
+                                       int32_t stages, int32_t passes, int32_t grid, void* out_cycles,
+                                       void* stream) {
+  using namespace fvtg;
+  if (stages < 1 || stages > 12 || (csize != 1 && csize != 2 && csize != 4) || nprod < 1 || nprod > 4 ||
+      stages % nprod || grid % csize)
+    return fail(FVTG_EINVAL, "probe3: bad arguments");
+  CUtensorMap tw;
+  FVTG_TRY(make_tmap_bf16(&tw, w_bf16, 2304, 256, 256, 128 / csize, 64));
+  const int smem = 12 * 16384 + 512 + 1024;
+  FVTG_CUDA_OK(cudaFuncSetAttribute(tma_stream_probe3_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  long long* oc = static_cast<long long*>(out_cycles);
+  FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, tma_stream_probe3_kernel, tw, csize, nprod, stages, passes, oc));
+  count_launch();
   return FVTG_OK;
 }

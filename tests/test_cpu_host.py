@@ -208,3 +208,13 @@ def test_synthetic_inputs_follow_the_loader_contract():
         np.testing.assert_allclose(v[i, :lv, -2].numpy(), np.arange(lv) / lv, atol=1e-6)    # TEF
         assert float(b["duration"][i]) == lv * cfg.clip_length
     assert b["src_vid_mask"].sum(1).int().tolist() == b["vid_len"].tolist()
+
+
+def test_product_never_imports_or_calls_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    import pathlib
+    import re
+    pkg = pathlib.Path(__file__).resolve().parent.parent / "flashvtg_b200"
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liboracle|oracle[./]", re.M)
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        assert not pat.search(p.read_text()), f"{p} references the oracle"
