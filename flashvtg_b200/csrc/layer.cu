@@ -1,39 +1,50 @@
 // Fused transformer-layer tail: everything of a post-norm layer that is row-wise, in ONE
 // persistent tcgen05 kernel per 128-row tile, with the 1024-wide hidden activations never leaving
-// the SM:
+// the SM (they never even reach shared memory):
 //
 //   z  = x + att . Wo^T + bo                         (out_proj + residual)
 //   T2V layer (transformer.py:359-367):  y = LN2( z  + W2 . PReLU(W1 . LN1(z) + b1) + b2 )
 //   SA  layer (transformer.py:416-420):  y = LN2( x1 + W2 . PReLU(W1 . x1 + b1) + b2 ),  x1 = LN1(z)
 //
-// Data flow per tile (TMEM: D_z = columns 0..255, D_h[2] = columns 256..383 / 384..511):
-//   TMA: att tile -> sA ; weight "units" ([128 rows][64 k] bf16, 16 KB) -> 5-stage ring
-//   MMA: D_z  = sA . Wo^T                                   (8 units)
-//   EPI: z = D_z + bo + x (fp32 residual stream, tile-blocked layout => coalesced 16 B / lane);
-//        LayerNorm1 -> bf16 -> sA (SWIZZLE_128B K-major, written by the epilogue threads);
-//        D_z <- z (T2V) or LN1(z) (SA) via tcgen05.st: the FFN residual lives in the accumulator
-//   for the 8 hidden pieces p of 128:   (ff1(p+1) is issued before ff2(p): MMA never waits on EPI)
-//        MMA: D_h[p&1] = sA . W1[p]^T                        (4 units)
-//        EPI: h = PReLU(D_h + b1[p]) -> bf16 -> sH[p&1]      (SWIZZLE_128B K-major)
-//        MMA: D_z += sH[p&1] . W2[:, p]^T                    (4 units; accumulates onto the residual)
-//   EPI: y = LayerNorm2(D_z + b2) -> fp32 residual stream, bf16(y), bf16(y + pos)
+// TMEM (512 columns): Z = columns 0..255 (FFN accumulator, initialised with the residual),
+//                     H = columns 256..511 = two 128-column hidden-piece accumulators H0 | H1;
+//                     the out_proj of a tile also accumulates in H (free between tiles), so it
+//                     overlaps the previous tile's final epilogue, which drains Z.
+// Shared memory: sA = 4 x [128 rows][64 k] bf16 SWIZZLE_128B units (att tile, then LN1 output),
+//                a 4-stage ring of 32 KB weight stages, LayerNorm statistics, per-layer vectors.
 //
-// 12 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue (two threads
-// per row: TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4).
+// Per tile:
+//   TMA : att tile -> sA ; weight stages: Wo[256 n][64 k] x4, then per hidden piece p (128 wide)
+//         W1[p] as 2 stages of 2 x [128 n][64 k], W2[:, p] as 2 stages of [256 n][64 k]
+//   MMA : H(0..255)  = sA . Wo^T                        16 x (128 x 256 x 16), operands in smem
+//   EPI1: z = H + bo + x (fp32 residual stream, tile-blocked layout => coalesced 16 B / lane);
+//         LayerNorm1 -> bf16 -> sA (written swizzled by the epilogue threads);
+//         Z <- z (T2V) or LN1(z) (SA) via tcgen05.st: the FFN residual lives in the accumulator
+//   for the 8 hidden pieces p:     (ff1(p+1), ff1(p+2) are issued before ff2(p): MMA rarely waits)
+//         MMA : H[p&1] = sA . W1[p]^T                    16 x (128 x 128 x 16)
+//         EPI2: h = PReLU(H[p&1] + b1[p]) -> bf16 pairs -> tcgen05.st back into the SAME columns
+//               (each thread overwrites only columns it alone has read)
+//         MMA : Z += h . W2[:, p]^T                      8 x (128 x 256 x 16), A operand from TMEM
+//   EPI3: y = LayerNorm2(Z + b2) -> fp32 residual stream, bf16(y), bf16(y + pos)
+//
+// 20 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 L2 prefetch of the next tile's
+// residual rows, 4..19 epilogue (four threads per row: TMEM lane quadrant = warp % 4, column
+// quarter = (warp - 4) / 4).
 #include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace fvtg {
 
-constexpr int LK_THREADS = 384;
-constexpr int LK_STAGES = 5;
-constexpr int LK_UNIT = 128 * 64 * 2;       // 16 KB: [128 rows][64 bf16], SWIZZLE_128B
-constexpr int LK_OFF_A = 0;                 // 4 units: att tile, then LN1 output
-constexpr int LK_OFF_H = 4 * LK_UNIT;       // 2 buffers x 2 units: hidden piece
-constexpr int LK_OFF_W = 8 * LK_UNIT;       // weight ring
-constexpr int LK_OFF_BAR = LK_OFF_W + LK_STAGES * LK_UNIT;
+constexpr int LK_THREADS = 640;
+constexpr int LK_EPI_THREADS = 512;
+constexpr int LK_STAGES = 4;
+constexpr int LK_UNIT = 128 * 64 * 2;        // 16 KB: [128 rows][64 bf16], SWIZZLE_128B
+constexpr int LK_STAGE = 2 * LK_UNIT;        // 32 KB
+constexpr int LK_OFF_A = 0;                  // 4 units: att tile, then LN1 output
+constexpr int LK_OFF_W = 4 * LK_UNIT;        // weight ring
+constexpr int LK_OFF_BAR = LK_OFF_W + LK_STAGES * LK_STAGE;
 constexpr int LK_OFF_STAT = LK_OFF_BAR + 256;
-constexpr int LK_OFF_PAR = LK_OFF_STAT + 2 * 2 * 128 * 8;
+constexpr int LK_OFF_PAR = LK_OFF_STAT + 2 * 4 * 128 * 8;   // [2 phases][4 quarters][128 rows] float2
 constexpr int LK_PAR_FLOATS = 256 * 3 + 1024 + 256 * 3;
 constexpr int LK_SMEM_BYTES = LK_OFF_PAR + LK_PAR_FLOATS * 4 + 1024 /*align slack*/;
 static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 KB limit");
@@ -45,7 +56,9 @@ static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 
       g.trace[((role) * 8 + it) * 32 + (ev)] = clock64();                               \
   } while (0)
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 __global__ void __launch_bounds__(LK_THREADS, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWo,
@@ -55,22 +68,19 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem + LK_OFF_A;
-  uint8_t* sH = smem + LK_OFF_H;
   uint8_t* sW = smem + LK_OFF_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LK_OFF_BAR);
-  uint64_t* full = bars;                    // [5] TMA -> MMA
-  uint64_t* empty = bars + LK_STAGES;       // [5] MMA -> TMA
-  uint64_t* a_full = bars + 10;             // att tile landed
-  uint64_t* a_empty = bars + 11;            // last ff1 MMA retired: sA reusable
-  uint64_t* z1_full = bars + 12;            // out_proj accumulated
-  uint64_t* z2_full = bars + 13;            // FFN accumulated
-  uint64_t* z_empty = bars + 14;            // final epilogue drained D_z
-  uint64_t* ln_ready = bars + 15;           // LN1 tile in sA, residual in D_z
-  uint64_t* hacc_full = bars + 16;          // [2] ff1 piece accumulated
-  uint64_t* h_ready = bars + 18;            // [2] hidden piece in sH, D_h drained
-  uint64_t* h_empty = bars + 20;            // [2] ff2 retired: sH reusable
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 24);
-  float2* s_stat = reinterpret_cast<float2*>(smem + LK_OFF_STAT);  // [2 phases][2 halves][128]
+  uint64_t* full = bars;                    // [4] TMA -> MMA
+  uint64_t* empty = bars + LK_STAGES;       // [4] MMA -> TMA
+  uint64_t* a_full = bars + 8;              // att tile landed in sA
+  uint64_t* a_empty = bars + 9;             // last ff1 MMA retired: sA reusable
+  uint64_t* z1_full = bars + 10;            // out_proj accumulated in H
+  uint64_t* z2_full = bars + 11;            // FFN accumulated in Z
+  uint64_t* ln_ready = bars + 12;           // LN1 tile in sA, residual in Z, H drained
+  uint64_t* hacc_full = bars + 13;          // [2] ff1 piece accumulated
+  uint64_t* h_ready = bars + 15;            // [2] bf16 hidden piece stored back into H[buf]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 20);
+  float2* s_stat = reinterpret_cast<float2*>(smem + LK_OFF_STAT);  // [2 phases][4 quarters][128]
   float* s_par = reinterpret_cast<float*>(smem + LK_OFF_PAR);
   float* s_bo = s_par;
   float* s_g1 = s_par + 256;
@@ -99,12 +109,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_init(a_empty, 1);
     mbar_init(z1_full, 1);
     mbar_init(z2_full, 1);
-    mbar_init(z_empty, 8);
-    mbar_init(ln_ready, 8);
+    mbar_init(ln_ready, 16);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&hacc_full[b], 1);
-      mbar_init(&h_ready[b], 8);
-      mbar_init(&h_empty[b], 1);
+      mbar_init(&h_ready[b], 16);
     }
     fence_mbar_init();
   }
@@ -125,32 +133,46 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  const uint32_t tmem_h = tmem + 256;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer --
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      auto unit = [&](const CUtensorMap* tm, int c0, int r0) {
+      auto stage_wait = [&]() -> uint8_t* {
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], LK_UNIT);
-        tma_load_2d(sW + s * LK_UNIT, tm, c0, r0, &full[s]);
+        mbar_expect_tx(&full[s], LK_STAGE);
+        return sW + s * LK_STAGE;
+      };
+      auto stage_next = [&]() {
         if (++s == LK_STAGES) { s = 0; ph ^= 1; }
       };
-      auto ff1 = [&](int p) {
-        for (int kb = 0; kb < 4; ++kb) unit(&tmW1, kb * 64, p * 128);
+      auto ff1 = [&](int p) {  // W1 rows p*128.., k-blocks (2h, 2h+1) per stage
+        for (int h = 0; h < 2; ++h) {
+          uint8_t* d = stage_wait();
+          tma_load_2d(d, &tmW1, (2 * h) * 64, p * 128, &full[s]);
+          tma_load_2d(d + LK_UNIT, &tmW1, (2 * h + 1) * 64, p * 128, &full[s]);
+          stage_next();
+        }
       };
-      auto ff2 = [&](int p) {
-        for (int kb2 = 0; kb2 < 2; ++kb2)
-          for (int nh = 0; nh < 2; ++nh) unit(&tmW2, p * 128 + kb2 * 64, nh * 128);
+      auto ff2 = [&](int p) {  // W2 all 256 rows, k-block p*128 + h*64
+        for (int h = 0; h < 2; ++h) {
+          uint8_t* d = stage_wait();
+          tma_load_2d(d, &tmW2, p * 128 + h * 64, 0, &full[s]);
+          stage_next();
+        }
       };
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         mbar_wait(a_empty, (it & 1) ^ 1);
         mbar_expect_tx(a_full, 4 * LK_UNIT);
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(sA + kb * LK_UNIT, &tmA, kb * 64, tile * 128, a_full);
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) unit(&tmWo, kb * 64, nh * 128);
+        for (int kb = 0; kb < 4; ++kb) {
+          uint8_t* d = stage_wait();
+          tma_load_2d(d, &tmWo, kb * 64, 0, &full[s]);
+          stage_next();
+        }
         ff1(0);
         ff1(1);
         for (int p = 0; p < 8; ++p) {
@@ -164,16 +186,15 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t idesc = umma_idesc_bf16(128, 128);
-      const uint32_t sA_u = smem_u32(sA), sH_u = smem_u32(sH), sW_u = smem_u32(sW);
-      auto unit = [&](uint32_t d_tmem, uint32_t a_addr, bool acc_first) {
+      const uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      const uint32_t idesc256 = umma_idesc_bf16(128, 256);
+      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+      auto stage_wait = [&]() -> uint32_t {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint64_t da = umma_desc_sw128(a_addr);
-        const uint64_t db = umma_desc_sw128(sW_u + s * LK_UNIT);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (acc_first || k > 0) ? 1u : 0u);
+        return sW_u + s * LK_STAGE;
+      };
+      auto stage_release = [&]() {
         umma_commit(&empty[s]);
         if (++s == LK_STAGES) { s = 0; ph ^= 1; }
       };
@@ -181,8 +202,19 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         auto ff1 = [&](int p) {
           const int buf = p & 1;
-          for (int kb = 0; kb < 4; ++kb)
-            unit(tmem + 256 + buf * 128, sA_u + kb * LK_UNIT, kb > 0);
+          const uint32_t d = tmem_h + buf * 128;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t w = stage_wait();
+#pragma unroll
+            for (int kbl = 0; kbl < 2; ++kbl) {
+              const uint64_t da = umma_desc_sw128(sA_u + (2 * h + kbl) * LK_UNIT);
+              const uint64_t db = umma_desc_sw128(w + kbl * LK_UNIT);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d, da + 2 * k, db + 2 * k, idesc128, (h | kbl | k) ? 1u : 0u);
+            }
+            stage_release();
+          }
           umma_commit(&hacc_full[buf]);
           if (p == 7) umma_commit(a_empty);
         };
@@ -191,19 +223,31 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t n = static_cast<uint32_t>(it) * 4u + static_cast<uint32_t>(p >> 1);
           mbar_wait(&h_ready[buf], n & 1u);
           tc_fence_after();
-          for (int kb2 = 0; kb2 < 2; ++kb2)
-            for (int nh = 0; nh < 2; ++nh)
-              unit(tmem + nh * 128, sH_u + buf * 2 * LK_UNIT + kb2 * LK_UNIT, true);
-          umma_commit(&h_empty[buf]);
+          const uint32_t a = tmem_h + buf * 128;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t w = stage_wait();
+            const uint64_t db = umma_desc_sw128(w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = h * 4 + k;  // K = 16 step of the piece: 8 packed columns of its thread quarter
+              umma_bf16_ts(tmem, a + 32 * (j >> 1) + 8 * (j & 1), db + 2 * k, idesc256, 1u);
+            }
+            stage_release();
+          }
         };
         LK_TRACE(0, 0);
-        mbar_wait(z_empty, (it & 1) ^ 1);
-        LK_TRACE(0, 1);
         mbar_wait(a_full, it & 1);
         tc_fence_after();
         LK_TRACE(0, 2);
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) unit(tmem + nh * 128, sA_u + kb * LK_UNIT, kb > 0);
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t w = stage_wait();
+          const uint64_t da = umma_desc_sw128(sA_u + kb * LK_UNIT);
+          const uint64_t db = umma_desc_sw128(w);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_h, da + 2 * k, db + 2 * k, idesc256, (kb | k) ? 1u : 0u);
+          stage_release();
+        }
         umma_commit(z1_full);
         LK_TRACE(0, 3);
         mbar_wait(ln_ready, it & 1);
@@ -222,76 +266,102 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         LK_TRACE(0, 22);
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------- L2 prefetch of the next tile's fp32 rows --
+    for (int tile = blockIdx.x + gridDim.x; tile < ntiles; tile += gridDim.x) {
+      const char* y = reinterpret_cast<const char*>(g.yf + static_cast<size_t>(tile) * (128 * 256));
+      for (int i = lane; i < 1024; i += 32) prefetch_l2(y + i * 128);
+      if (g.out_pb && g.pos && g.pos_mod <= 0) {
+        const char* ps = reinterpret_cast<const char*>(g.pos + static_cast<size_t>(tile) * (128 * 256));
+        for (int i = lane; i < 1024; i += 32) prefetch_l2(ps + i * 128);
+      }
+      // pace: one tile ahead is enough; wait for this CTA's epilogue to reach the tile before it
+      // (cheap heuristic: the warp simply yields for a while)
+      __nanosleep(20000);
+    }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue --
     const int ew = warp - 4;
     const int q = ew & 3;    // TMEM lane quadrant (== warp % 4)
-    const int hf = ew >> 2;  // column half
+    const int qt = ew >> 2;  // column quarter
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t u[32];
-    float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int row = tile * 128 + r;
       const bool inb = row < g.M;
       // fp32 residual stream, tile-blocked: [tile][col/4][row%128][4]
       float* yblk = g.yf + static_cast<size_t>(tile) * (128 * 256) + r * 4;
-
-      // ---- epilogue 1: z = D_z + bo + x ; LayerNorm1 -> sA ; residual back into D_z ----------
       const bool tr = (warp == 4 && lane == 0);
+
+      // ---- epilogue 1: z = H + bo + x ; LayerNorm1 -> sA ; FFN residual into Z -----------------
       if (tr) LK_TRACE(1, 0);
+      float4 rr[8];
+      {  // the first residual chunk does not depend on the MMA: fetch it before waiting
+        const int c0 = qt * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rr[i] = inb ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(z1_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 1);
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = hf * 128 + c * 32;
-        tmem_ld32(tmem + lane_addr + c0, u);
-        float4 rr[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          rr[i] = inb ? *reinterpret_cast<const float4*>(yblk + ((c0 >> 2) + i) * 512)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = qt * 64 + c * 32;
+        tmem_ld32(tmem_h + lane_addr + c0, u);
+        if (c == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            rr[i] = inb ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          v[4 * i + 0] = __uint_as_float(u[4 * i + 0]) + s_bo[c0 + 4 * i + 0] + rr[i].x;
-          v[4 * i + 1] = __uint_as_float(u[4 * i + 1]) + s_bo[c0 + 4 * i + 1] + rr[i].y;
-          v[4 * i + 2] = __uint_as_float(u[4 * i + 2]) + s_bo[c0 + 4 * i + 2] + rr[i].z;
-          v[4 * i + 3] = __uint_as_float(u[4 * i + 3]) + s_bo[c0 + 4 * i + 3] + rr[i].w;
+          const float4 b = ld_f4(s_bo + c0 + 4 * i);
+          u[4 * i + 0] = __float_as_uint(__uint_as_float(u[4 * i + 0]) + b.x + rr[i].x);
+          u[4 * i + 1] = __float_as_uint(__uint_as_float(u[4 * i + 1]) + b.y + rr[i].y);
+          u[4 * i + 2] = __float_as_uint(__uint_as_float(u[4 * i + 2]) + b.z + rr[i].z);
+          u[4 * i + 3] = __float_as_uint(__uint_as_float(u[4 * i + 3]) + b.w + rr[i].w);
         }
-        if (c == 0) shift = v[0];
+        if (c == 0) shift = __uint_as_float(u[0]);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float d = v[j] - shift;
+          const float d = __uint_as_float(u[j]) - shift;
           s1 += d;
           s2 += d * d;
-          u[j] = __float_as_uint(v[j]);
         }
         tmem_st32(tmem + lane_addr + c0, u);
       }
       tmem_st_wait();
       if (tr) LK_TRACE(1, 2);
-      s_stat[hf * 128 + r] = make_float2(shift + s1 * (1.f / 128.f), s2 - s1 * s1 * (1.f / 128.f));
+      // per-quarter partial: (mean of 64, centred sum of squares of 64)
+      s_stat[qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
       epi_bar_sync();
       float mean, rstd;
       {
-        const float2 a = s_stat[r], b = s_stat[128 + r];
-        const float dm = a.x - b.x;
-        mean = 0.5f * (a.x + b.x);
-        const float var = fmaxf((a.y + b.y + dm * dm * 64.f) * (1.f / 256.f), 0.f);
-        rstd = rsqrtf(var + 1e-5f);
+        const float2 a0 = s_stat[r], a1 = s_stat[128 + r], a2 = s_stat[256 + r], a3 = s_stat[384 + r];
+        mean = 0.25f * (a0.x + a1.x + a2.x + a3.x);
+        const float d0 = a0.x - mean, d1 = a1.x - mean, d2 = a2.x - mean, d3 = a3.x - mean;
+        const float m2 = a0.y + a1.y + a2.y + a3.y + 64.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+        rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
       }
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = hf * 128 + c * 32;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = qt * 64 + c * 32;
         tmem_ld32(tmem + lane_addr + c0, u);
         tmem_ld_wait();
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = (__uint_as_float(u[j]) - mean) * rstd * s_g1[c0 + j] + s_be1[c0 + j];
+        for (int i = 0; i < 8; ++i) {
+          const float4 gm = ld_f4(s_g1 + c0 + 4 * i), bt = ld_f4(s_be1 + c0 + 4 * i);
+          v[4 * i + 0] = (__uint_as_float(u[4 * i + 0]) - mean) * rstd * gm.x + bt.x;
+          v[4 * i + 1] = (__uint_as_float(u[4 * i + 1]) - mean) * rstd * gm.y + bt.y;
+          v[4 * i + 2] = (__uint_as_float(u[4 * i + 2]) - mean) * rstd * gm.z + bt.z;
+          v[4 * i + 3] = (__uint_as_float(u[4 * i + 3]) - mean) * rstd * gm.w + bt.w;
+        }
         st_shared_bf16x32(sA + (c0 >> 6) * LK_UNIT, r, (c0 & 63) >> 3, v);
         if (g.mode == LAYER_SA) {
 #pragma unroll
@@ -306,91 +376,106 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(ln_ready);
       if (tr) LK_TRACE(1, 3);
 
-      // ---- epilogue 2 (x8): hidden piece = PReLU(D_h + b1) -> sH ------------------------------
+      // ---- epilogue 2 (x8): hidden piece = PReLU(H[buf] + b1) -> bf16 pairs back into H[buf] --
 #pragma unroll 1
       for (int p = 0; p < 8; ++p) {
         const int buf = p & 1;
         const uint32_t n = static_cast<uint32_t>(it) * 4u + static_cast<uint32_t>(p >> 1);
         mbar_wait(&hacc_full[buf], n & 1u);
-        mbar_wait(&h_empty[buf], (n & 1u) ^ 1u);
         tc_fence_after();
         if (tr) LK_TRACE(1, 4 + 2 * p);
-        uint8_t* hu = sH + buf * 2 * LK_UNIT + hf * LK_UNIT;  // k-block hf of the piece
+        const uint32_t ha = tmem_h + lane_addr + buf * 128 + qt * 32;
+        tmem_ld32(ha, u);
+        tmem_ld_wait();
+        const float* bb = s_b1 + p * 128 + qt * 32;
+        uint32_t hp[16];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int c0 = hf * 64 + c * 32;
-          tmem_ld32(tmem + lane_addr + 256 + buf * 128 + c0, u);
-          tmem_ld_wait();
-          const float* bb = s_b1 + p * 128 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(u[j]) + bb[j];
-            v[j] = x > 0.f ? x : g.prelu * x;
-          }
-          st_shared_bf16x32(hu, r, c * 4, v);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = ld_f4(bb + 4 * i);
+          float x0 = __uint_as_float(u[4 * i + 0]) + b.x;
+          float x1 = __uint_as_float(u[4 * i + 1]) + b.y;
+          float x2 = __uint_as_float(u[4 * i + 2]) + b.z;
+          float x3 = __uint_as_float(u[4 * i + 3]) + b.w;
+          x0 = x0 > 0.f ? x0 : g.prelu * x0;
+          x1 = x1 > 0.f ? x1 : g.prelu * x1;
+          x2 = x2 > 0.f ? x2 : g.prelu * x2;
+          x3 = x3 > 0.f ? x3 : g.prelu * x3;
+          hp[2 * i + 0] = pack_bf16(x0, x1);
+          hp[2 * i + 1] = pack_bf16(x2, x3);
         }
-        fence_proxy_async_smem();
+        tmem_st16(ha, hp);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_ready[buf]);
         if (tr) LK_TRACE(1, 5 + 2 * p);
       }
 
-      // ---- final epilogue: y = LayerNorm2(D_z + b2) -> residual stream / bf16 operands --------
+      // ---- final epilogue: y = LayerNorm2(Z + b2) -> residual stream / bf16 operands --------
+      int prow = row;
+      if (g.pos_mod > 0) prow = row % g.pos_mod;
+      const bool st_pos = g.out_pb && inb && (g.pos_rowlim <= 0 || prow < g.pos_rowlim);
+      const bool ld_pos = st_pos && g.pos;
       mbar_wait(z2_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 20);
       shift = 0.f; s1 = 0.f; s2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = hf * 128 + c * 32;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = qt * 64 + c * 32;
         tmem_ld32(tmem + lane_addr + c0, u);
         tmem_ld_wait();
         if (c == 0) shift = __uint_as_float(u[0]) + s_b2[c0];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(u[j]) + s_b2[c0 + j] - shift;
-          s1 += d;
-          s2 += d * d;
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = ld_f4(s_b2 + c0 + 4 * i);
+          const float d0 = __uint_as_float(u[4 * i + 0]) + b.x - shift;
+          const float d1 = __uint_as_float(u[4 * i + 1]) + b.y - shift;
+          const float d2 = __uint_as_float(u[4 * i + 2]) + b.z - shift;
+          const float d3 = __uint_as_float(u[4 * i + 3]) + b.w - shift;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
       }
-      s_stat[256 + hf * 128 + r] = make_float2(shift + s1 * (1.f / 128.f), s2 - s1 * s1 * (1.f / 128.f));
+      s_stat[512 + qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
       epi_bar_sync();
       if (tr) LK_TRACE(1, 21);
       {
-        const float2 a = s_stat[256 + r], b = s_stat[256 + 128 + r];
-        const float dm = a.x - b.x;
-        mean = 0.5f * (a.x + b.x);
-        const float var = fmaxf((a.y + b.y + dm * dm * 64.f) * (1.f / 256.f), 0.f);
-        rstd = rsqrtf(var + 1e-5f);
+        const float2 a0 = s_stat[512 + r], a1 = s_stat[640 + r], a2 = s_stat[768 + r], a3 = s_stat[896 + r];
+        mean = 0.25f * (a0.x + a1.x + a2.x + a3.x);
+        const float d0 = a0.x - mean, d1 = a1.x - mean, d2 = a2.x - mean, d3 = a3.x - mean;
+        const float m2 = a0.y + a1.y + a2.y + a3.y + 64.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+        rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
       }
-      int prow = row;
-      if (g.pos_mod > 0) prow = row % g.pos_mod;
-      const bool st_pos = g.out_pb && inb && (g.pos_rowlim <= 0 || prow < g.pos_rowlim);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = hf * 128 + c * 32;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = qt * 64 + c * 32;
         tmem_ld32(tmem + lane_addr + c0, u);
-        float4 pp[8];
-        if (st_pos && g.pos) {
+        if (ld_pos) {
           if (g.pos_mod > 0) {
             const float* ps = g.pos + static_cast<size_t>(prow) * 256 + c0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pp[i] = *reinterpret_cast<const float4*>(ps + 4 * i);
+            for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + 4 * i);
           } else {
             const float* ps = g.pos + static_cast<size_t>(tile) * (128 * 256) + r * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              pp[i] = *reinterpret_cast<const float4*>(ps + ((c0 >> 2) + i) * 512);
+            for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + ((c0 >> 2) + i) * 512);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 8; ++i) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = (__uint_as_float(u[j]) + s_b2[c0 + j] - mean) * rstd * s_g2[c0 + j] + s_be2[c0 + j];
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = ld_f4(s_b2 + c0 + 4 * i), gm = ld_f4(s_g2 + c0 + 4 * i),
+                       bt = ld_f4(s_be2 + c0 + 4 * i);
+          v[4 * i + 0] = (__uint_as_float(u[4 * i + 0]) + b.x - mean) * rstd * gm.x + bt.x;
+          v[4 * i + 1] = (__uint_as_float(u[4 * i + 1]) + b.y - mean) * rstd * gm.y + bt.y;
+          v[4 * i + 2] = (__uint_as_float(u[4 * i + 2]) + b.z - mean) * rstd * gm.z + bt.z;
+          v[4 * i + 3] = (__uint_as_float(u[4 * i + 3]) + b.w - mean) * rstd * gm.w + bt.w;
+        }
         if (inb) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -400,18 +485,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (st_pos) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              v[4 * i + 0] += pp[i].x;
-              v[4 * i + 1] += pp[i].y;
-              v[4 * i + 2] += pp[i].z;
-              v[4 * i + 3] += pp[i].w;
+              v[4 * i + 0] += rr[i].x;
+              v[4 * i + 1] += rr[i].y;
+              v[4 * i + 2] += rr[i].z;
+              v[4 * i + 3] += rr[i].w;
             }
             st_global_bf16x32(g.out_pb + static_cast<size_t>(row) * 256 + c0, v);
           }
         }
       }
+      // Z is rewritten next by this same thread (epilogue 1 of the next tile), H by MMAs that
+      // are ordered behind ln_ready: no further hand-off is needed here.
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(z_empty);
       if (tr) LK_TRACE(1, 22);
     }
   }
@@ -435,9 +520,9 @@ int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w
   }
   CUtensorMap ta, two, tw1, tw2;
   FVTG_TRY(make_tmap_bf16(&ta, att, args.M, 256, 256, 128, 64));
-  FVTG_TRY(make_tmap_bf16(&two, wo, 256, 256, 256, 128, 64));
+  FVTG_TRY(make_tmap_bf16(&two, wo, 256, 256, 256, 256, 64));
   FVTG_TRY(make_tmap_bf16(&tw1, w1, 1024, 256, 256, 128, 64));
-  FVTG_TRY(make_tmap_bf16(&tw2, w2, 256, 1024, 1024, 128, 64));
+  FVTG_TRY(make_tmap_bf16(&tw2, w2, 256, 1024, 1024, 256, 64));
   const int tiles = (args.M + 127) / 128;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(st, PC_LAYER);

@@ -182,6 +182,91 @@ class FlashVTGB200(torch.nn.Module):
                           count, nms_c, launches)
 
     @torch.no_grad()
+    def infer_host(self, src_vid: torch.Tensor, vid_len: torch.Tensor, src_txt: torch.Tensor,
+                   txt_len: torch.Tensor, duration: Optional[torch.Tensor] = None,
+                   nms: Optional[str] = "normal", nms_thd: Optional[float] = None,
+                   device: Optional[torch.device] = None, chunk_videos: int = 128,
+                   out: Optional[dict] = None) -> dict:
+        """Whole hot path for HOST (ideally pinned) inputs: the batch is cut into chunks whose
+        host->device copies (copy stream) overlap the kernels of the previous chunk (current
+        stream), two device slots deep; the ranked spans / saliency come back in one
+        device->host copy per field.  Returns host tensors {boundary, windows, nms_windows,
+        nms_order, count, nms_count, saliency, t2vattn}; blocks until they are readable.
+        This is the call bench.py times as `e2e` (what inference.py's eval loop does per batch:
+        prepare_batch_inputs' .to(device), forward, .cpu())."""
+        cfg = self.cfg
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if src_vid.is_cuda or src_txt.is_cuda:
+            raise ValueError("infer_host takes host tensors; use infer() for device tensors")
+        B, Lv, _ = src_vid.shape
+        Lt = src_txt.shape[1]
+        if duration is None:
+            duration = vid_len.to(torch.float32) * cfg.clip_length
+        topk = cfg.max_num_moment
+        do_nms = _NMS_MODES[nms] != _lib.NMS_NONE
+        if out is None:
+            def pin(*shape, dtype=torch.float32):
+                return torch.empty(*shape, dtype=dtype).pin_memory()
+            out = {"boundary": pin(B, topk, 3), "windows": pin(B, topk, 3),
+                   "count": pin(B, dtype=torch.int32), "saliency": pin(B, Lv), "t2vattn": pin(B, Lv)}
+            if do_nms:
+                out.update({"nms_windows": pin(B, topk, 3), "nms_order": pin(B, topk, dtype=torch.int32),
+                            "nms_count": pin(B, dtype=torch.int32)})
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            key = (dev.index, "copy_stream")
+            if key not in self._ws:
+                self._ws[key] = torch.cuda.Stream(device=dev)
+            cp = self._ws[key]
+            cb = max(1, min(chunk_videos, B))
+            slots = self._host_slots(dev, cb, Lv, Lt)
+            free_ev = [None, None]
+            pending = []
+            cp.wait_stream(cur)
+            for i, b0 in enumerate(range(0, B, cb)):
+                nb = min(cb, B - b0)
+                sl = slots[i & 1]
+                with torch.cuda.stream(cp):
+                    if free_ev[i & 1] is not None:
+                        cp.wait_event(free_ev[i & 1])
+                    sl["src_vid"][:nb].copy_(src_vid[b0:b0 + nb], non_blocking=True)
+                    sl["src_txt"][:nb].copy_(src_txt[b0:b0 + nb], non_blocking=True)
+                    sl["vid_len"][:nb].copy_(vid_len[b0:b0 + nb], non_blocking=True)
+                    sl["txt_len"][:nb].copy_(txt_len[b0:b0 + nb], non_blocking=True)
+                    sl["duration"][:nb].copy_(duration[b0:b0 + nb], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(cp)
+                cur.wait_event(ready)
+                r = self.infer(sl["src_vid"][:nb], sl["vid_len"][:nb], sl["src_txt"][:nb],
+                               sl["txt_len"][:nb], duration=sl["duration"][:nb], nms=nms, nms_thd=nms_thd)
+                free_ev[i & 1] = torch.cuda.Event()
+                free_ev[i & 1].record(cur)
+                pending.append((b0, nb, r))
+                for name, t in (("boundary", r.boundary), ("windows", r.windows), ("count", r.count),
+                                ("saliency", r.saliency), ("t2vattn", r.t2vattn),
+                                ("nms_windows", r.nms_windows), ("nms_order", r.nms_order),
+                                ("nms_count", r.nms_count)):
+                    if t is not None and name in out:
+                        out[name][b0:b0 + nb].copy_(t, non_blocking=True)
+            cur.synchronize()
+        out["launches"] = sum(r.launches for _, _, r in pending)
+        return out
+
+    def _host_slots(self, dev: torch.device, cb: int, Lv: int, Lt: int):
+        key = (dev.index, "host_slots", cb, Lv, Lt)
+        if key not in self._ws:
+            cfg = self.cfg
+
+            def slot():
+                return {"src_vid": torch.empty(cb, Lv, cfg.v_feat_dim, dtype=torch.float32, device=dev),
+                        "src_txt": torch.empty(cb, Lt, cfg.t_feat_dim, dtype=torch.float32, device=dev),
+                        "vid_len": torch.empty(cb, dtype=torch.int32, device=dev),
+                        "txt_len": torch.empty(cb, dtype=torch.int32, device=dev),
+                        "duration": torch.empty(cb, dtype=torch.float32, device=dev)}
+            self._ws[key] = (slot(), slot())
+        return self._ws[key]
+
+    @torch.no_grad()
     def decode(self, cls_logit: torch.Tensor, conf_logit: torch.Tensor, coord: torch.Tensor,
                vid_len: torch.Tensor, Lv: int, duration: Optional[torch.Tensor] = None,
                nms: Optional[str] = "normal", nms_thd: Optional[float] = None):

@@ -320,3 +320,26 @@ def test_full_size_properties_b1024():
     out2, order2, _ = temporal_nms(rb.nms_windows, rb.nms_count, cfg.nms_thd, "normal")
     assert torch.equal(out2, rb.nms_windows)
     assert rb.launches > 0
+
+
+def test_infer_host_pipeline_equals_device_call():
+    """The host-buffer entry (chunked H2D overlapped with compute on a second stream, the call
+    bench.py times as e2e) returns bit-identical results to one device-resident infer()."""
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS
+    cfg = PRESETS["qvh_iv2"]
+    sd = synth.make_state_dict(cfg, 2025, spread=True)
+    batch = synth.make_inputs(cfg, 11, 75, 32, seed=9, ragged=True, min_lv=9)
+    m, r = _run(cfg, sd, batch)
+    host = {k: v.pin_memory() for k, v in batch.items()}
+    for chunk in (3, 4, 64):
+        o = m.infer_host(host["src_vid"], host["vid_len"], host["src_txt"], host["txt_len"],
+                         duration=host["duration"], nms="normal", chunk_videos=chunk)
+        for name in ("boundary", "windows", "nms_windows", "nms_order", "count", "nms_count",
+                     "saliency", "t2vattn"):
+            assert torch.equal(o[name], getattr(r, name).cpu()), f"{name} differs at chunk {chunk}"
+        assert o["launches"] > 0
+    # second call reusing the pinned result buffers
+    o2 = m.infer_host(host["src_vid"], host["vid_len"], host["src_txt"], host["txt_len"],
+                      duration=host["duration"], nms="normal", chunk_videos=4, out=o)
+    assert torch.equal(o2["nms_windows"], r.nms_windows.cpu())
