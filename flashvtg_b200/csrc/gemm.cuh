@@ -79,6 +79,7 @@ struct GemmArgs {
   int ntaps, kb_per_tap;
   int tap_shift[GEMM_MAX_TAPS];
   int a_switch_ntile;  // n-tiles >= this read A from the second tensor map
+  long long* trace;    // debug (fvtg_dbg_gemm only): clock64 stamps of CTA 0, [role 3][tile 16][event 8] at +1024
   GemmEpi epi;
 };
 

@@ -65,8 +65,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
              const __grid_constant__ LayerArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ symbol (an integer round trip
+  // would demote every later access to a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem + LK_OFF_A;
   uint8_t* sW = smem + LK_OFF_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LK_OFF_BAR);
