@@ -36,6 +36,7 @@ struct LayerArgs {
   int pos_mod;
   int pos_rowlim;    // > 0: out_pb only for rows with row % pos_mod < pos_rowlim
   long long* trace;  // debug: per-phase clock64 stamps of CTA 0 (fvtg_dbg_set_trace), null in production
+  int dbg;           // debug (env FVTG_LAYER_DBG): bit 0 skip residual loads, bit 1 skip pos loads, bit 2 skip global stores
 };
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args);

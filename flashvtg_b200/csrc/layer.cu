@@ -269,16 +269,23 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 3) {
     // ------------------------------------- L2 prefetch of the next tile's fp32 rows --
-    for (int tile = blockIdx.x + gridDim.x; tile < ntiles; tile += gridDim.x) {
-      const char* y = reinterpret_cast<const char*>(g.yf + static_cast<size_t>(tile) * (128 * 256));
-      for (int i = lane; i < 1024; i += 32) prefetch_l2(y + i * 128);
-      if (g.out_pb && g.pos && g.pos_mod <= 0) {
-        const char* ps = reinterpret_cast<const char*>(g.pos + static_cast<size_t>(tile) * (128 * 256));
-        for (int i = lane; i < 1024; i += 32) prefetch_l2(ps + i * 128);
+    // The residual / position tiles are contiguous 128 KB blocks (tile-blocked layout): one lane
+    // asks the TMA engine to pull the next tile of this CTA into L2 while the current tile's FFN
+    // keeps the tensor pipe busy, so epilogue 1 / 3 find their operands in L2 instead of HBM.
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int nxt = tile + gridDim.x;
+        mbar_wait(ln_ready, it & 1);   // epilogue 1 of `tile` is done: its loads are out of the way
+        if (nxt < ntiles && !(g.dbg & 8)) {
+          const char* y = reinterpret_cast<const char*>(g.yf + static_cast<size_t>(nxt) * (128 * 256));
+          for (int i = 0; i < 8; ++i) bulk_prefetch_l2(y + i * 16384, 16384);
+          if (g.out_pb && g.pos && g.pos_mod <= 0) {
+            const char* ps = reinterpret_cast<const char*>(g.pos + static_cast<size_t>(nxt) * (128 * 256));
+            for (int i = 0; i < 8; ++i) bulk_prefetch_l2(ps + i * 16384, 16384);
+          }
+        }
       }
-      // pace: one tile ahead is enough; wait for this CTA's epilogue to reach the tile before it
-      // (cheap heuristic: the warp simply yields for a while)
-      __nanosleep(20000);
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue --
@@ -292,6 +299,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int row = tile * 128 + r;
       const bool inb = row < g.M;
+      const bool ldres = inb && !(g.dbg & 1);
       // fp32 residual stream, tile-blocked: [tile][col/4][row%128][4]
       float* yblk = g.yf + static_cast<size_t>(tile) * (128 * 256) + r * 4;
       const bool tr = (warp == 4 && lane == 0);
@@ -303,7 +311,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c0 = qt * 64;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          rr[i] = inb ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rr[i] = ldres ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(z1_full, it & 1);
       tc_fence_after();
@@ -316,7 +324,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (c == 1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            rr[i] = inb ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[i] = ldres ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
 #pragma unroll
@@ -416,7 +424,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int prow = row;
       if (g.pos_mod > 0) prow = row % g.pos_mod;
       const bool st_pos = g.out_pb && inb && (g.pos_rowlim <= 0 || prow < g.pos_rowlim);
-      const bool ld_pos = st_pos && g.pos;
+      const bool ld_pos = st_pos && g.pos && !(g.dbg & 2);
       mbar_wait(z2_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 20);
@@ -477,22 +485,25 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           v[4 * i + 2] = (__uint_as_float(u[4 * i + 2]) + b.z - mean) * rstd * gm.z + bt.z;
           v[4 * i + 3] = (__uint_as_float(u[4 * i + 3]) + b.w - mean) * rstd * gm.w + bt.w;
         }
-        if (inb) {
+        const bool st_ok = inb && !(g.dbg & 4);
+        if (st_ok) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(yblk + ((c0 >> 2) + i) * 512) =
                 make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          if (g.out_b) st_global_bf16x32(g.out_b + static_cast<size_t>(row) * 256 + c0, v);
-          if (st_pos) {
+        }
+        if (g.out_b)
+          st_global_bf16x32_paired(g.out_b + static_cast<size_t>(row) * 256 + c0, 256, st_ok, v);
+        if (g.out_pb) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i + 0] += rr[i].x;
-              v[4 * i + 1] += rr[i].y;
-              v[4 * i + 2] += rr[i].z;
-              v[4 * i + 3] += rr[i].w;
-            }
-            st_global_bf16x32(g.out_pb + static_cast<size_t>(row) * 256 + c0, v);
+          for (int i = 0; i < 8; ++i) {
+            v[4 * i + 0] += rr[i].x;
+            v[4 * i + 1] += rr[i].y;
+            v[4 * i + 2] += rr[i].z;
+            v[4 * i + 3] += rr[i].w;
           }
+          st_global_bf16x32_paired(g.out_pb + static_cast<size_t>(row) * 256 + c0, 256,
+                                   st_pos && !(g.dbg & 4), v);
         }
       }
       // Z is rewritten next by this same thread (epilogue 1 of the next tile), H by MMAs that
@@ -526,8 +537,13 @@ int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w
   FVTG_TRY(make_tmap_bf16(&tw2, w2, 256, 1024, 1024, 256, 64));
   const int tiles = (args.M + 127) / 128;
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  LayerArgs a2 = args;
+  {
+    const char* d = getenv("FVTG_LAYER_DBG");
+    a2.dbg = d ? atoi(d) : 0;
+  }
   ProfScope prof(st, PC_LAYER);
-  layer_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, st>>>(ta, two, tw1, tw2, args);
+  layer_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, st>>>(ta, two, tw1, tw2, a2);
   FVTG_LAUNCH_CHECK("layer_kernel");
   return FVTG_OK;
 }

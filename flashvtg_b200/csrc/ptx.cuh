@@ -286,4 +286,41 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// TMA-engine prefetch of a contiguous global range into L2 (bytes: multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+}  // namespace fvtg
+
+namespace fvtg {
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+                 "r"(r[7])
+               : "memory");
+}
+// Row-major bf16 store of 32 consecutive columns per lane (lane = row) with half the sectors and
+// a quarter of the store wavefronts of four 16-byte stores per lane: lanes pair up (2i, 2i+1),
+// swap one 32-byte half through a shuffle, and each lane then writes one full 32-byte sector of
+// the pair's first row and one of its second row (256-bit stores), so a row's 64 bytes are
+// written by two adjacent lanes.  `dst` = element (row of THIS lane, first column), 32-byte
+// aligned; `pitch` in elements; `ok` = this lane's row is to be stored.  All 32 lanes must call.
+__device__ __forceinline__ void st_global_bf16x32_paired(__nv_bfloat16* dst, int pitch, bool ok,
+                                                         const float* y) {
+  const int lane = threadIdx.x & 31;
+  const int m = lane & 1;
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16(y[2 * i], y[2 * i + 1]);
+  uint32_t rcv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rcv[i] = __shfl_xor_sync(0xffffffffu, m ? w[i] : w[8 + i], 1);
+  const bool ok0 = __shfl_sync(0xffffffffu, ok, lane & ~1);
+  const bool ok1 = __shfl_sync(0xffffffffu, ok, lane | 1);
+  // first row of the pair: lane 0 holds its own columns 0..15, lane 1 received lane 0's 16..31
+  __nv_bfloat16* row0 = dst - m * pitch + m * 16;
+  if (ok0) st_global_v8(row0, m ? rcv : w);
+  // second row: lane 0 received lane 1's columns 0..15, lane 1 holds its own 16..31
+  if (ok1) st_global_v8(row0 + pitch, m ? w + 8 : rcv);
+}
 }  // namespace fvtg
