@@ -36,10 +36,14 @@ struct LayerArgs {
   int pos_mod;
   int pos_rowlim;    // > 0: out_pb only for rows with row % pos_mod < pos_rowlim
   long long* trace;  // debug: per-phase clock64 stamps of CTA 0 (fvtg_dbg_set_trace), null in production
+  int stagger_ns;    // start-up delay step: cluster c sleeps (c % 8) * stagger_ns before its first tile
   int dbg;           // debug (env FVTG_LAYER_DBG): bit 0 skip residual loads, bit 1 skip pos loads, bit 2 skip global stores
 };
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args);
+// same contract on CTA pairs (cta_group::2 MMAs, weight tiles split between the two SMs of a TPC)
+int launch_layer_pair(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
+                      const LayerArgs& args);
 
 // fp32 tile-blocked rows -> row-major fp32: dst[(b * rows_out + j)][256] = src row (b * rows_in + j), j < rows_out
 int launch_unblock(cudaStream_t st, const float* src_blk, float* dst, int B, int rows_in, int rows_out);

@@ -111,14 +111,6 @@ mma_rate_probe_kernel(int N, int iters, int nbuf, long long* out_cycles) {
 // cluster multicast.  Every CTA of a cluster of `csize` loads rows [rank*128/csize, ...) of each
 // 16 KB unit and multicasts the slice to all CTAs; nprod producer lanes (different warps) split
 // the unit stream.  Consumer releases each stage to every CTA of the cluster.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
@@ -197,6 +189,61 @@ tma_stream_probe3_kernel(const __grid_constant__ CUtensorMap tmW, int csize, int
   if (threadIdx.x == 0) out_cycles[blockIdx.x] = clock64() - t0;
 }
 
+
+// tcgen05.mma issue-rate floor for the four operand flavours the layer kernel uses:
+// cg = 1 / 2 (CTA pair, cluster launch), ts = 0 (A in shared memory) / 1 (A in TMEM).
+template <int cg>
+__global__ void __launch_bounds__(128, 1)
+mma_rate_probe2_kernel(int N, int iters, int ts, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t holder;
+  for (int i = threadIdx.x; i < 12 * 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  uint32_t rank = 0;
+  if constexpr (cg == 2) rank = cluster_ctarank();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) {
+    if constexpr (cg == 2) { tmem_alloc_cg2(&holder, 512); tmem_relinquish_cg2(); }
+    else { tmem_alloc(&holder, 512); tmem_relinquish(); }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (cg == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = holder;
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = umma_idesc_bf16(cg == 2 ? 256 : 128, N);
+    const uint32_t base = smem_u32(smem);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint64_t da = umma_desc_sw128(base + (i & 3) * 16384);
+      const uint64_t db = umma_desc_sw128(base + 4 * 16384 + (i & 1) * 32768);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (cg == 2) {
+          if (ts) umma_bf16_ts_cg2(tmem, tmem + 256 + 8 * k + 32 * (i & 3), db + 2 * k, idesc, 1u);
+          else umma_bf16_cg2(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+        } else {
+          if (ts) umma_bf16_ts(tmem, tmem + 256 + 8 * k + 32 * (i & 3), db + 2 * k, idesc, 1u);
+          else umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+        }
+      }
+    }
+    if constexpr (cg == 2) umma_commit_cg2(&bar, 1); else umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    out_cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (cg == 2) cluster_sync_all();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    if constexpr (cg == 2) tmem_dealloc_cg2(tmem, 512); else tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace fvtg
 
 extern "C" int32_t fvtg_dbg_tma_probe(const void* w_bf16 /* [rows][256] */, int32_t rows, int32_t stages,
@@ -258,6 +305,35 @@ extern "C" int32_t fvtg_dbg_tma_probe3(const void* w_bf16 /* [2304][256] */, int
   cfg.numAttrs = 1;
   long long* oc = static_cast<long long*>(out_cycles);
   FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, tma_stream_probe3_kernel, tw, csize, nprod, stages, passes, oc));
+  count_launch();
+  return FVTG_OK;
+}
+
+extern "C" int32_t fvtg_dbg_mma_probe2(int32_t N, int32_t iters, int32_t cg, int32_t ts, int32_t grid,
+                                       void* out_cycles, void* stream) {
+  using namespace fvtg;
+  if ((N != 128 && N != 256) || (cg != 1 && cg != 2) || grid % cg) return fail(FVTG_EINVAL, "mma probe2: bad arguments");
+  const int smem = 12 * 16384 + 1024;
+  FVTG_CUDA_OK(cudaFuncSetAttribute(mma_rate_probe2_kernel<1>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FVTG_CUDA_OK(cudaFuncSetAttribute(mma_rate_probe2_kernel<2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cg;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cg == 2 ? 1 : 0;
+  long long* oc = static_cast<long long*>(out_cycles);
+  if (cg == 2) FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, mma_rate_probe2_kernel<2>, N, iters, ts, oc));
+  else FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, mma_rate_probe2_kernel<1>, N, iters, ts, oc));
   count_launch();
   return FVTG_OK;
 }

@@ -384,3 +384,34 @@ def test_forward_matches_oracle_at_baseline_shapes(preset, B, Lv, Lt, ragged):
         assert cnt == min(n, cfg.max_num_moment)
         sc = r.boundary[b, :cnt, 2].cpu().numpy()
         assert np.all(np.diff(sc) <= 0)
+
+
+def test_cta_pair_layer_kernel_matches_default():
+    """The cta_group::2 variant of the fused layer kernel (FVTG_LAYER_PAIR=1, kept for A/B
+    measurements) computes the same forward as the default single-CTA kernel."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from flashvtg_b200 import synth
+from flashvtg_b200.config import PRESETS
+from flashvtg_b200.model import FlashVTGB200
+cfg = PRESETS["qvh_iv2"]
+m = FlashVTGB200(cfg).eval(); m.load_state_dict(synth.make_state_dict(cfg, 2025, spread=True))
+b = synth.make_inputs(cfg, 9, 75, 32, seed=11, ragged=True, min_lv=7)
+dev = torch.device("cuda:0")
+r = m.infer(b["src_vid"].to(dev), b["vid_len"].to(dev), b["src_txt"].to(dev), b["txt_len"].to(dev),
+            duration=b["duration"].to(dev), want_heads=True)
+torch.save({"sal": r.saliency.cpu(), "cls": r.cls_logit.cpu(), "coord": r.coord.cpu(), "t2v": r.t2vattn.cpu()}, sys.argv[1])
+''' % ROOT
+    import tempfile
+    outs = []
+    for pair in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, FVTG_LAYER_PAIR=pair)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            outs.append(torch.load(f.name))
+    for k in outs[0]:
+        e = max_rel(outs[1][k].numpy(), outs[0][k].numpy())
+        assert e < 2e-3, f"{k}: pair vs default max-norm rel err {e:.3e}"
