@@ -105,6 +105,30 @@ __device__ __forceinline__ void add_f32x32(const float* base, size_t row, int c0
       g.trace[1024 + ((role) * 16 + it) * 8 + (ev)] = clock64();                  \
   } while (0)
 
+// v[0..31] = u[0..31] + bias[0..31] with 16-byte shared-memory loads
+__device__ __forceinline__ void add_bias32(const uint32_t* u, const float* bias, float* v) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = b4[i];
+    v[4 * i + 0] = __uint_as_float(u[4 * i + 0]) + b.x;
+    v[4 * i + 1] = __uint_as_float(u[4 * i + 1]) + b.y;
+    v[4 * i + 2] = __uint_as_float(u[4 * i + 2]) + b.z;
+    v[4 * i + 3] = __uint_as_float(u[4 * i + 3]) + b.w;
+  }
+}
+// activation with the switch outside the element loop (act is uniform for the launch)
+__device__ __forceinline__ void act32(float* v, int act, float slope) {
+  if (act == ACT_NONE) return;
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], slope);
+  }
+}
+
 __device__ __forceinline__ void gemm_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -278,11 +302,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int c0 = hf * 128 + c * 32;
             tmem_ld32(tacc + c0, u);
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) + s_bias[c0 + j];
+            add_bias32(u, s_bias + c0, v);
             if (has_res) add_f32x32(e.res, row, c0, blk, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], slope);
+            act32(v, e.act, slope);
             if (c == 0) shift = v[0];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -313,15 +335,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
           if (ln) {
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+            const float4* be4 = reinterpret_cast<const float4*>(s_beta + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = (__uint_as_float(u[j]) - mean) * rstd * s_gamma[c0 + j] + s_beta[c0 + j];
+            for (int i = 0; i < 8; ++i) {
+              const float4 gm = g4[i], bt = be4[i];
+              v[4 * i + 0] = (__uint_as_float(u[4 * i + 0]) - mean) * rstd * gm.x + bt.x;
+              v[4 * i + 1] = (__uint_as_float(u[4 * i + 1]) - mean) * rstd * gm.y + bt.y;
+              v[4 * i + 2] = (__uint_as_float(u[4 * i + 2]) - mean) * rstd * gm.z + bt.z;
+              v[4 * i + 3] = (__uint_as_float(u[4 * i + 3]) - mean) * rstd * gm.w + bt.w;
+            }
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) + s_bias[c0 + j];
+            add_bias32(u, s_bias + c0, v);
             if (has_res) add_f32x32(e.res, row, c0, blk, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], slope);
+            act32(v, e.act, slope);
           }
           if (e.post_relu) {
 #pragma unroll
@@ -349,13 +376,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else if (e.mode == EPI_TILE) {
+        // lean inner loops: 16-byte bias loads, the activation switch hoisted out of the element loop
         for (int c0 = hf * HC; c0 < (hf + 1) * HC; c0 += 32) {
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
+          add_bias32(u, s_bias + n0 + c0, v);
+          act32(v, e.act, slope);
+          if (!ri.valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = apply_act(__uint_as_float(u[j]) + s_bias[n0 + c0 + j], slope);
-            v[j] = ri.valid ? x : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           st_shared_bf16x32(stage_out + (c0 >> 6) * GEMM_A_BYTES, r, (c0 & 63) >> 3, v);
         }
@@ -364,9 +393,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+          const float4* w4 = reinterpret_cast<const float4*>(s_dotw + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            dot += fmaxf(__uint_as_float(u[j]) + s_bias[c0 + j], 0.f) * s_dotw[c0 + j];
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = b4[i], w = w4[i];
+            dot += fmaxf(__uint_as_float(u[4 * i + 0]) + b.x, 0.f) * w.x;
+            dot += fmaxf(__uint_as_float(u[4 * i + 1]) + b.y, 0.f) * w.y;
+            dot += fmaxf(__uint_as_float(u[4 * i + 2]) + b.z, 0.f) * w.z;
+            dot += fmaxf(__uint_as_float(u[4 * i + 3]) + b.w, 0.f) * w.w;
+          }
         }
         if (hf == 1) s_stat[r].x = dot;
         gemm_epi_bar();

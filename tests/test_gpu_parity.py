@@ -52,8 +52,10 @@ def test_gemm_against_torch(lib):
     import ctypes as C
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
+    # the last four are tall enough (> 148 m-tiles) for the weight-resident mode of the short-K GEMMs
     for (M, N, K) in [(128, 256, 64), (300, 256, 256), (9600, 256, 832), (2400, 1024, 256),
-                      (5000, 128, 256), (18944, 256, 1280)]:
+                      (5000, 128, 256), (18944, 256, 1280), (40000, 768, 256), (38001, 256, 256),
+                      (45000, 128, 256), (41000, 128, 128)]:
         a = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
         w = (torch.randn(N, K, device=dev) * 0.1).to(torch.bfloat16)
         bias = torch.randn(N, device=dev)
