@@ -192,10 +192,11 @@ def run_ours(args):
             for k, v in base.items()}
     d_in = {k: v.to(dev) for k, v in host.items()}
     B = B_PER_GPU
+    uniform = bool((host["vid_len"] == host["vid_len"][0]).all())   # known on the host: no device sync
 
     def step_device():
         r = model.infer(d_in["src_vid"], d_in["vid_len"], d_in["src_txt"], d_in["txt_len"],
-                        duration=d_in["duration"], nms="normal")
+                        duration=d_in["duration"], nms="normal", uniform_len=uniform)
         if world > 1:
             # the only collective of the path: gather the ranked-span records of every shard
             gather_records({"nms_windows": r.nms_windows, "count": r.count, "saliency": r.saliency},
@@ -287,7 +288,7 @@ def run_ours(args):
         ksteps = max(2, min(args.steps, 5))
         for _ in range(ksteps):
             model.infer(d_in["src_vid"], d_in["vid_len"], d_in["src_txt"], d_in["txt_len"],
-                        duration=d_in["duration"], nms="normal")
+                        duration=d_in["duration"], nms="normal", uniform_len=uniform)
         torch.cuda.synchronize()
         n_cls = len(_lib.PROF_CLASSES)
         ms_c = (C.c_double * n_cls)()

@@ -75,7 +75,7 @@ class FvtgWeights(C.Structure):
 
 
 class FvtgBatch(C.Structure):
-    _fields_ = [("B", i32), ("Lv", i32), ("Lt", i32), ("_pad", i32),
+    _fields_ = [("B", i32), ("Lv", i32), ("Lt", i32), ("uniform_vid_len", i32),
                 ("vid", vp), ("txt", vp), ("vid_len", vp), ("txt_len", vp)]
 
 

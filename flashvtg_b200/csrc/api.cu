@@ -163,7 +163,7 @@ static LayerArgs layer_args(const FvtgEncLayer& L, int rows, int mode, float* yf
 // out_b / out_pb: bf16(x) and bf16(x + pos) for the next layer's V and Q/K projections.
 static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, int Lseq, float* xf,
                     const bf16* xb, const bf16* xpb, bf16* out_b, bf16* out_pb, const float* pos,
-                    int pos_mod, int pos_rowlim, const int* klen_src, int kbase) {
+                    int pos_mod, int pos_rowlim, const int* klen_src, int kbase, int pos_cmp_L = 0) {
   const int rows = B * Lseq;
   {  // Q,K from x+pos ; V from x  (in_proj rows 0:512 / 512:768)
     GemmArgs g = gemm_args(rows, 768, 256, 256);
@@ -190,6 +190,7 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
   a.out_pb = out_pb;
   a.pos = pos;
   a.pos_mod = pos_mod;
+  a.pos_cmp_L = pos_cmp_L;
   a.pos_rowlim = pos_rowlim;
   return launch_layer(st, w.att, static_cast<const bf16*>(L.out_proj.w),
                       static_cast<const bf16*>(L.ff1.w), static_cast<const bf16*>(L.ff2.w), a);
@@ -198,7 +199,7 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
 // One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396):
 // attention over the constant [dummies ‖ text] keys, then the fused layer kernel.
 static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, const Ws& w, int B,
-                     int Lv, int S, const int* tlen, bool want_b, int layer) {
+                     int Lv, int S, const int* tlen, bool want_b, int layer, int pos_cmp_L) {
   const int rows = B * Lv;
   {
     AttnArgs a;
@@ -216,6 +217,7 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
   a.out_b = want_b ? w.Yb : nullptr;
   a.out_pb = w.YPb;
   a.pos = w.pos_v;
+  a.pos_cmp_L = pos_cmp_L;
   return launch_layer(st, w.att, static_cast<const bf16*>(L.out_proj.w),
                       static_cast<const bf16*>(L.ff1.w), static_cast<const bf16*>(L.ff2.w), a);
 }
@@ -246,9 +248,12 @@ static int in_proj(cudaStream_t st, const FvtgInProj& P, const Ws& w, const floa
 static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W, const Ws& w,
                         int B, int Lv, int Lt, const float* vid, const float* txt,
                         const int* vlen, const int* tlen, float* video_emb, float* saliency,
-                        float* t2v, float* dummy_tokens) {
+                        float* t2v, float* dummy_tokens, bool uniform_vlen) {
   const int nd = c.num_dummies, S = nd + Lt;
-  FVTG_TRY(launch_posenc(st, w.pos_v, vlen, B, Lv));
+  // uniform-length chunk (caller's promise, FvtgBatch.uniform_vid_len; always true for one video):
+  // the sine table shrinks from B*Lv rows to Lv rows that stay cache resident
+  const int pos_cmp_L = (uniform_vlen || B == 1) ? Lv : 0;
+  FVTG_TRY(launch_posenc(st, w.pos_v, vlen, B, Lv, pos_cmp_L > 0));
   FVTG_TRY(launch_fill_dummy(st, W.dummy_tok, W.dummy_pos, w.Xf, w.Xb, w.XPb, w.pos_d, B, S, nd));
   {  // text: rows scattered into the [dummies ‖ text] stream, plus the constant text keys/values
     GemmEpi e;
@@ -263,6 +268,7 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
     memset(&e, 0, sizeof(e));
     e.f32_blocked = 1;
     e.out_f32 = w.Yf; e.out_bf16 = w.Yb; e.out_bf16_pos = w.YPb; e.pos = w.pos_v;
+    e.pos_cmp_L = pos_cmp_L;
     FVTG_TRY(in_proj(st, W.vid, w, vid, w.vid_b, B * Lv, c.v_dim, c.v_dim_pad, e));
   }
   for (int i = 0; i < c.dummy_layers; ++i) {
@@ -273,11 +279,11 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
   }
   if (dummy_tokens) FVTG_TRY(launch_unblock(st, w.Xf, dummy_tokens, B, S, nd));
   for (int i = 0; i < c.t2v_layers; ++i)
-    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1, i));
+    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1, i, pos_cmp_L));
   for (int i = 0; i < c.enc_layers; ++i) {
     const bool last = i == c.enc_layers - 1;
     FVTG_TRY(sa_layer(st, W.enc[i], w, B, Lv, w.Yf, w.Yb, w.YPb, last ? nullptr : w.Yb,
-                      last ? nullptr : w.YPb, w.pos_v, 0, 0, vlen, 0));
+                      last ? nullptr : w.YPb, w.pos_v, 0, 0, vlen, 0, pos_cmp_L));
   }
   FVTG_TRY(launch_saliency(st, w.Yf, vlen, W.sal_w1, W.sal_b1, W.sal_w2t, W.sal_b2, w.tsum,
                            c.t2v_layers, w.sal_scratch, saliency, t2v, B, Lv));
@@ -461,7 +467,8 @@ int32_t fvtg_fusion_fwd(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatc
         out->video_emb ? out->video_emb + static_cast<size_t>(b0) * Lv * 256 : nullptr,
         out->saliency + static_cast<size_t>(b0) * Lv,
         out->t2v ? out->t2v + static_cast<size_t>(b0) * Lv : nullptr,
-        out->dummy_tokens ? out->dummy_tokens + static_cast<size_t>(b0) * nd * 256 : nullptr));
+        out->dummy_tokens ? out->dummy_tokens + static_cast<size_t>(b0) * nd * 256 : nullptr,
+        in->uniform_vid_len != 0));
   }
   return FVTG_OK;
 }
@@ -557,7 +564,8 @@ int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* 
         fout->video_emb ? fout->video_emb + static_cast<size_t>(b0) * Lv * 256 : nullptr,
         fout->saliency + static_cast<size_t>(b0) * Lv,
         fout->t2v ? fout->t2v + static_cast<size_t>(b0) * Lv : nullptr,
-        fout->dummy_tokens ? fout->dummy_tokens + static_cast<size_t>(b0) * nd * 256 : nullptr));
+        fout->dummy_tokens ? fout->dummy_tokens + static_cast<size_t>(b0) * nd * 256 : nullptr,
+        in->uniform_vid_len != 0));
     float* cls = keep_heads ? hout->cls_logit + static_cast<size_t>(b0) * g0.n_max : ws.cls;
     float* conf = keep_heads ? hout->conf_logit + static_cast<size_t>(b0) * g0.n_max : ws.conf;
     float* coord = keep_heads ? hout->coord + static_cast<size_t>(b0) * g0.n_max * 2 : ws.coord;

@@ -370,7 +370,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (e.out_x2) st_global_bf16x32(e.out_x2 + static_cast<size_t>(ri.x2) * 256 + c0, v);
             }
             if (st_pos) {
-              if (e.pos) add_f32x32(e.pos, prow, c0, blk && e.pos_mod <= 0, v);
+              if (e.pos && e.pos_cmp_L > 0) {
+                const float* pc = e.pos + (static_cast<size_t>(c0 >> 2) * e.pos_cmp_L + row % e.pos_cmp_L) * 4;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 p4 = *reinterpret_cast<const float4*>(pc + static_cast<size_t>(q) * e.pos_cmp_L * 4);
+                  v[q * 4 + 0] += p4.x; v[q * 4 + 1] += p4.y; v[q * 4 + 2] += p4.z; v[q * 4 + 3] += p4.w;
+                }
+              } else if (e.pos) add_f32x32(e.pos, prow, c0, blk && e.pos_mod <= 0, v);
               st_global_bf16x32(e.out_bf16_pos + o, v);
             }
           }

@@ -56,6 +56,7 @@ struct GemmEpi {
   bf16* out_bf16_pos;  // [rows][256] or null: bf16(y + pos[row])
   const float* pos;    // fp32 [*][256] or null (treated as zero)
   int pos_mod;         // pos row = row % pos_mod when > 0
+  int pos_cmp_L;       // > 0: pos is the compact table [64][pos_cmp_L][4] indexed by row % pos_cmp_L
   int pos_rowlim;      // when > 0: out_bf16_pos only for rows with row % pos_mod < pos_rowlim
   bf16* out_x1;        // extra bf16 destinations (RM_TXT: Kc; RM_CHAIN final: H1 / H2)
   bf16* out_x2;

@@ -12,7 +12,8 @@ int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const f
                    bf16* out, int rows, int dim, int dim_pad);
 // Sine position table (position_encoding.py:61-72) for every video row of the chunk:
 // pos fp32 [B*Lv][256] in the tile-blocked layout; rows >= vlen[b] are zero.
-int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv);
+// compact: all videos of the chunk share vlen[0] -> pos is the [64][Lv][4] table (see prep.cu)
+int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv, bool compact);
 // Initial dummy-encoder stream: rows [b*S + j], j < nd, of X (fp32, tile-blocked), Xb = bf16(X),
 // XPb = bf16(X + dummy_pos); and the [dummy_pos ‖ 0] position table pos_d fp32 [S][256].
 int launch_fill_dummy(cudaStream_t st, const float* dtok, const float* dpos, float* X, bf16* Xb,
@@ -34,6 +35,7 @@ struct LayerArgs {
   bf16* out_pb;      // bf16(y + pos) [M][256] or null
   const float* pos;  // pos_mod == 0: tile-blocked per-row table ; > 0: row-major [pos_mod][256] ; null = 0
   int pos_mod;
+  int pos_cmp_L;     // > 0: pos is the compact table [64][pos_cmp_L][4], row -> row % pos_cmp_L (uniform-length chunk)
   int pos_rowlim;    // > 0: out_pb only for rows with row % pos_mod < pos_rowlim
   long long* trace;  // debug: per-phase clock64 stamps of CTA 0 (fvtg_dbg_set_trace), null in production
   int stagger_ns;    // start-up delay step: cluster c sleeps (c % 8) * stagger_ns before its first tile

@@ -27,8 +27,7 @@
 //         MMA : Z += h . W2[:, p]^T                      8 x (128 x 256 x 16), A operand from TMEM
 //   EPI3: y = LayerNorm2(Z + b2) -> fp32 residual stream, bf16(y), bf16(y + pos)
 //
-// 20 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 L2 prefetch of the next tile's
-// residual rows, 4..19 epilogue (four threads per row: TMEM lane quadrant = warp % 4, column
+// 20 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..19 epilogue (four threads per row: TMEM lane quadrant = warp % 4, column
 // quarter = (warp - 4) / 4).
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -274,26 +273,6 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         LK_TRACE(0, 22);
       }
     }
-  } else if (warp == 3) {
-    // ------------------------------------- L2 prefetch of the next tile's fp32 rows --
-    // The residual / position tiles are contiguous 128 KB blocks (tile-blocked layout): one lane
-    // asks the TMA engine to pull the next tile of this CTA into L2 while the current tile's FFN
-    // keeps the tensor pipe busy, so epilogue 1 / 3 find their operands in L2 instead of HBM.
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int nxt = tile + gridDim.x;
-        mbar_wait(ln_ready, it & 1);   // epilogue 1 of `tile` is done: its loads are out of the way
-        if (nxt < ntiles && !(g.dbg & 8)) {
-          const char* y = reinterpret_cast<const char*>(g.yf + static_cast<size_t>(nxt) * (128 * 256));
-          for (int i = 0; i < 8; ++i) bulk_prefetch_l2(y + i * 16384, 16384);
-          if (g.out_pb && g.pos && g.pos_mod <= 0) {
-            const char* ps = reinterpret_cast<const char*>(g.pos + static_cast<size_t>(nxt) * (128 * 256));
-            for (int i = 0; i < 8; ++i) bulk_prefetch_l2(ps + i * 16384, 16384);
-          }
-        }
-      }
-    }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue --
     const int ew = warp - 4;
@@ -472,6 +451,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const float* ps = g.pos + static_cast<size_t>(prow) * 256 + c0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + 4 * i);
+          } else if (g.pos_cmp_L > 0) {
+            const float* ps = g.pos + (static_cast<size_t>(c0 >> 2) * g.pos_cmp_L + row % g.pos_cmp_L) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + static_cast<size_t>(i) * g.pos_cmp_L * 4);
           } else {
             const float* ps = g.pos + static_cast<size_t>(tile) * (128 * 256) + r * 4;
 #pragma unroll

@@ -489,6 +489,10 @@ layer_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float* ps = g.pos + static_cast<size_t>(prow) * 256 + c0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) rr[i] = lp_ld_f4(ps + 4 * i);
+          } else if (g.pos_cmp_L > 0) {
+            const float* ps = g.pos + (static_cast<size_t>(c0 >> 2) * g.pos_cmp_L + row % g.pos_cmp_L) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = lp_ld_f4(ps + static_cast<size_t>(i) * g.pos_cmp_L * 4);
           } else {
             const float* ps = g.pos + static_cast<size_t>(tile) * (128 * 256) + r * 4;
 #pragma unroll

@@ -165,8 +165,33 @@ __global__ void posenc_kernel(float* __restrict__ pos, const int* __restrict__ v
   *reinterpret_cast<float4*>(pos + (tile * 64 + c4) * 512 + rin * 4) = v;
 }
 
-int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv) {
+// Compact table for a chunk whose videos all have the same true length vlen[0] (the pos rows
+// depend on (position, length) only): pos_c[col/4][i][4], i < Lv; rows >= vlen[0] are zero.  Lanes
+// of a warp read consecutive rows of one column group -> 16-byte loads stay contiguous.
+__global__ void posenc_compact_kernel(float* __restrict__ pos, const int* __restrict__ vlen, int Lv) {
+  const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tt >= Lv * 64) return;
+  const int c4 = tt / Lv, i = tt - c4 * Lv;
+  const int len = vlen[0];
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < len) {
+    const float e = static_cast<float>(i + 1) / (static_cast<float>(len) + 1e-6f) * 6.283185307179586f;
+    const float w0 = powf(10000.f, static_cast<float>(4 * c4) / 256.f);
+    const float w1 = powf(10000.f, static_cast<float>(4 * c4 + 2) / 256.f);
+    const float a0 = e / w0, a1 = e / w1;
+    v = make_float4(sinf(a0), cosf(a0), sinf(a1), cosf(a1));
+  }
+  *reinterpret_cast<float4*>(pos + (static_cast<size_t>(c4) * Lv + i) * 4) = v;
+}
+
+int launch_posenc(cudaStream_t st, float* pos, const int* vlen, int B, int Lv, bool compact) {
   if (B * Lv <= 0) return FVTG_OK;
+  if (compact) {
+    ProfScope prof(st, PC_OTHER);
+    posenc_compact_kernel<<<(Lv * 64 + 255) / 256, 256, 0, st>>>(pos, vlen, Lv);
+    FVTG_LAUNCH_CHECK("posenc_compact_kernel");
+    return FVTG_OK;
+  }
   const long long rows_pad = ((static_cast<long long>(B) * Lv + 127) / 128) * 128;
   const long long threads = rows_pad * 64;
   ProfScope prof(st, PC_OTHER);

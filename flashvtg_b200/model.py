@@ -114,8 +114,11 @@ class FlashVTGB200(torch.nn.Module):
               txt_len: torch.Tensor, duration: Optional[torch.Tensor] = None,
               nms: Optional[str] = "normal", nms_thd: Optional[float] = None,
               want_heads: bool = False, want_emb: bool = False,
-              want_dummy: bool = False) -> FvtgResult:
+              want_dummy: bool = False, uniform_len: bool = False) -> FvtgResult:
         """Whole hot path for B videos on the current CUDA stream (no host sync).
+
+        uniform_len=True is the caller's promise that every video has the same true length
+        (vid_len[b] == vid_len[0]); the position table is then built for Lv rows only.
 
         src_vid fp32 (B, Lv, Dv) with TEF appended, src_txt fp32 (B, Lt, Dt), vid_len / txt_len
         int32 (B,) true lengths, duration fp32 (B,) seconds (default vid_len * clip_length)."""
@@ -161,7 +164,7 @@ class FlashVTGB200(torch.nn.Module):
             nms_o = torch.empty(B, topk, **i32) if do_nms else None
             nms_c = torch.empty(B, **i32) if do_nms else None
 
-            batch = _lib.FvtgBatch(B, Lv, Lt, 0, src_vid.data_ptr(), src_txt.data_ptr(),
+            batch = _lib.FvtgBatch(B, Lv, Lt, int(bool(uniform_len) or B == 1), src_vid.data_ptr(), src_txt.data_ptr(),
                                    vid_len.data_ptr(), txt_len.data_ptr())
             fout = _lib.FvtgFusionOut(_lib.ptr(emb), sal.data_ptr(), t2v.data_ptr(), _lib.ptr(dummy))
             hout = _lib.FvtgHeadsOut(n_max, 0, _lib.ptr(cls), _lib.ptr(conf), _lib.ptr(coord))
@@ -237,8 +240,10 @@ class FlashVTGB200(torch.nn.Module):
                     ready = torch.cuda.Event()
                     ready.record(cp)
                 cur.wait_event(ready)
+                hv = vid_len[b0:b0 + nb]   # host copy: uniform-length chunks take the compact position table
                 r = self.infer(sl["src_vid"][:nb], sl["vid_len"][:nb], sl["src_txt"][:nb],
-                               sl["txt_len"][:nb], duration=sl["duration"][:nb], nms=nms, nms_thd=nms_thd)
+                               sl["txt_len"][:nb], duration=sl["duration"][:nb], nms=nms, nms_thd=nms_thd,
+                               uniform_len=bool((hv == hv[0]).all()))
                 free_ev[i & 1] = torch.cuda.Event()
                 free_ev[i & 1].record(cur)
                 pending.append((b0, nb, r))

@@ -138,7 +138,9 @@ typedef struct FvtgWeights {
 /* One batch of B videos / queries.  Ragged semantics: video b is processed with its own
  * true lengths vid_len[b] <= Lv, txt_len[b] <= Lt exactly as the reference would at bs=1. */
 typedef struct FvtgBatch {
-  int32_t B, Lv, Lt, _pad;
+  int32_t B, Lv, Lt;
+  int32_t uniform_vid_len; /* hint: 1 = the caller guarantees vid_len[b] == vid_len[0] for all b (the sine
+                              position table is then built once for Lv rows instead of per video); 0 = may differ */
   const float* vid;       /* fp32 [B][Lv][v_dim]  (src_vid, TEF appended) */
   const float* txt;       /* fp32 [B][Lt][t_dim]  (src_txt) */
   const int32_t* vid_len; /* [B] */

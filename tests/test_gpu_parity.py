@@ -417,3 +417,29 @@ torch.save({"sal": r.saliency.cpu(), "cls": r.cls_logit.cpu(), "coord": r.coord.
     for k in outs[0]:
         e = max_rel(outs[1][k].numpy(), outs[0][k].numpy())
         assert e < 2e-3, f"{k}: pair vs default max-norm rel err {e:.3e}"
+
+
+def test_uniform_length_hint_changes_nothing():
+    """FvtgBatch.uniform_vid_len (compact sine table for chunks whose videos share one length) is a
+    pure layout optimisation: bit-identical outputs with and without the hint, full and short length."""
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS
+    cfg = PRESETS["qvh_iv2"]
+    sd = synth.make_state_dict(cfg, 2025, spread=True)
+    dev = torch.device("cuda:0")
+    m = _model(cfg, sd)
+    for lv_true in (75, 41):
+        batch = synth.make_inputs(cfg, 5, 75, 32, seed=21, ragged=False)
+        if lv_true != 75:   # shorter than the padded length, still uniform
+            batch["vid_len"][:] = lv_true
+            batch["src_vid"][:, lv_true:] = 0
+            batch["duration"][:] = lv_true * cfg.clip_length
+        outs = []
+        for hint in (False, True):
+            r = m.infer(batch["src_vid"].to(dev), batch["vid_len"].to(dev), batch["src_txt"].to(dev),
+                        batch["txt_len"].to(dev), duration=batch["duration"].to(dev), want_heads=True,
+                        uniform_len=hint)
+            torch.cuda.synchronize()
+            outs.append(r)
+        for name in ("saliency", "t2vattn", "cls_logit", "conf_logit", "coord", "boundary", "nms_windows"):
+            assert torch.equal(getattr(outs[0], name), getattr(outs[1], name)), (lv_true, name)
