@@ -176,6 +176,8 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
   const int b = blockIdx.x >> 1, hg = blockIdx.x & 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  pdl_launch_dependents();
+  pdl_wait();
   int klen = a.kbase + a.klen_src[b];
   if (klen > a.Lk) klen = a.Lk;
   const int col0 = hg * 128;
@@ -332,7 +334,7 @@ static int launch_attn_video(cudaStream_t st, const AttnArgs& a, int LqPad, size
     set = smem;
   }
   ProfScope prof(st, PC_ATTN);
-  attn_video_kernel<NT, KV_SHARED><<<a.B * 2, 256, smem, st>>>(a, LqPad);
+  FVTG_CUDA_OK(launch_pdl(attn_video_kernel<NT, KV_SHARED>, dim3(a.B * 2), dim3(256), smem, st, a, LqPad));
   FVTG_LAUNCH_CHECK("attn_video_kernel");
   return FVTG_OK;
 }

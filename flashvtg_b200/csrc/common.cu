@@ -1,5 +1,6 @@
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace fvtg {
@@ -53,6 +54,11 @@ void prof_begin(cudaStream_t st, int cls) {
 void prof_end(cudaStream_t st) {
   ProfState& p = prof_state();
   if (!p.recs.empty()) cudaEventRecord(p.recs.back().b, st);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("FVTG_PDL"); return !e || atoi(e) != 0; }();
+  return on;
 }
 
 int check_arch() {

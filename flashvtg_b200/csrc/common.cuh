@@ -66,6 +66,27 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_end(st); }
 };
 
+// Kernel launch with programmatic stream serialisation: the kernel's prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the tail of the previous kernel of the stream; the
+// kernel itself calls pdl_wait() before it touches anything a predecessor wrote (ptx.cuh).
+bool pdl_enabled();  // env FVTG_PDL (default on)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int check_arch();  // FVTG_OK iff the current device is sm_100
 int sm_count();
 

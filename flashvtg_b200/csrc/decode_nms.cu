@@ -11,7 +11,7 @@
 
 namespace fvtg {
 
-constexpr int DEC_THREADS = 256;
+constexpr int DEC_THREADS = 128;  // 54 regs x 128 threads: 9 CTAs per SM, so 1024 videos fit one wave
 constexpr int NMS_MAX = FVTG_MAX_TOPK;  // 64 rows
 
 struct NmsSmem {
@@ -42,61 +42,74 @@ __device__ __forceinline__ bool sorts_before(float sa, int pa, float sb, int pb)
 
 // post_processing_mr_nms on n <= 64 rows held in shared memory; executed by one full warp.
 // mode 0 normal / 1 linear.  Results in o_* (final order) and o_src (source row of each).
+// Order-preserving key of a score for torch.argmax semantics: NaN is the maximum, -0.0 == +0.0.
+__device__ __forceinline__ unsigned score_key(float v) {
+  if (v != v) return 0xFFFFFFFFu;
+  if (v == 0.f) return 0x80000000u;
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 __device__ void nms_f32_warp(NmsSmem& S, int n, float thd, int mode, int lane) {
-  for (int i = 0; i < n; ++i) {
-    // first argmax over rows [i, n): NaN counts as the maximum (torch.argmax)
-    float bv = 0.f;
-    int bi = 1 << 30;
-    bool bn = false;
-    for (int r = i + lane; r < n; r += 32) {
-      const float v = S.sc[r];
-      const bool vn = v != v;
-      bool take;
-      if (bi == (1 << 30)) take = true;
-      else if (vn != bn) take = vn;
-      else if (!vn && v != bv) take = v > bv;
-      else take = false;  // equal (or both NaN): keep the earlier index
-      if (take) { bv = v; bi = r; bn = vn; }
-    }
+  // Rows stay in registers (lane l owns rows l and l + 32); the reference's row swaps
+  // (nncore.swap_element) are tracked as a position per row, so one step of its serial loop -
+  // first argmax over positions >= i, swap, IoU suppression of the positions behind - is four
+  // warp reductions (redux.sync) plus two IoU evaluations per lane, with no shared-memory traffic.
+  const unsigned FULL = 0xffffffffu;
+  float st[2] = {0.f, 0.f}, ed[2] = {0.f, 0.f}, sc[2] = {0.f, 0.f};
+  int sr[2] = {0, 0};
+  unsigned pos[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // current position of the row; 0xFFFFFFFF = no row
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const bool on = ov != ov;
-      bool take;
-      if (oi == (1 << 30)) take = false;
-      else if (bi == (1 << 30)) take = true;
-      else if (on != bn) take = on;
-      else if (!on && ov != bv) take = ov > bv;
-      else take = oi < bi;
-      if (take) { bv = ov; bi = oi; bn = on; }
+  for (int h = 0; h < 2; ++h) {
+    const int r = lane + 32 * h;
+    if (r < n) { st[h] = S.st[r]; ed[h] = S.ed[r]; sc[h] = S.sc[r]; sr[h] = S.src[r]; pos[h] = r; }
+  }
+  for (int i = 0; i < n; ++i) {
+    // first argmax over positions [i, n): largest key, then smallest position
+    unsigned k[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) k[h] = (pos[h] != 0xFFFFFFFFu && pos[h] >= static_cast<unsigned>(i)) ? score_key(sc[h]) : 0u;
+    const unsigned kmax = __reduce_max_sync(FULL, k[0] > k[1] ? k[0] : k[1]);
+    unsigned cand = 0xFFFFFFFFu;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (pos[h] != 0xFFFFFFFFu && pos[h] >= static_cast<unsigned>(i) && k[h] == kmax && pos[h] < cand) cand = pos[h];
+    const unsigned bpos = __reduce_min_sync(FULL, cand);   // position of the selected row
+    // the selected row's window, broadcast from its owner; then the swap of positions i <-> bpos
+    unsigned sb = 0u, eb = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (pos[h] == bpos) { sb = __float_as_uint(st[h]); eb = __float_as_uint(ed[h]); }
+    const float s0 = __uint_as_float(__reduce_or_sync(FULL, sb));
+    const float e0 = __uint_as_float(__reduce_or_sync(FULL, eb));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (pos[h] == bpos) pos[h] = i;
+      else if (pos[h] == static_cast<unsigned>(i)) pos[h] = bpos;
     }
-    if (lane == 0 && bi != i) {
-      float t;
-      int ti;
-      t = S.st[i]; S.st[i] = S.st[bi]; S.st[bi] = t;
-      t = S.ed[i]; S.ed[i] = S.ed[bi]; S.ed[bi] = t;
-      t = S.sc[i]; S.sc[i] = S.sc[bi]; S.sc[bi] = t;
-      ti = S.src[i]; S.src[i] = S.src[bi]; S.src[bi] = ti;
-    }
-    __syncwarp();
-    const float s0 = S.st[i], e0 = S.ed[i];
+    // suppression of the rows behind position i against the selected row
     const float a0 = __fsub_rn(e0, s0);
-    for (int r = i + 1 + lane; r < n; r += 32) {
-      const float s1 = S.st[r], e1 = S.ed[r];
-      const float a1 = __fsub_rn(e1, s1);
-      float inter = __fsub_rn(fminf(e0, e1), fmaxf(s0, s1));
-      if (inter < 0.f) inter = 0.f;  // clamp(min=0), NaN stays NaN
-      const float uni = __fsub_rn(__fadd_rn(a0, a1), inter);
-      const float iou = __fdiv_rn(inter, uni);
-      if (mode == FVTG_NMS_NORMAL) {
-        if (iou >= thd) S.sc[r] = 0.f;  // NaN compares false: kept
-      } else {
-        S.sc[r] = __fmul_rn(S.sc[r], __fsub_rn(1.f, iou));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (pos[h] != 0xFFFFFFFFu && pos[h] > static_cast<unsigned>(i)) {
+        const float a1 = __fsub_rn(ed[h], st[h]);
+        float inter = __fsub_rn(fminf(e0, ed[h]), fmaxf(s0, st[h]));
+        if (inter < 0.f) inter = 0.f;  // clamp(min=0), NaN stays NaN
+        const float uni = __fsub_rn(__fadd_rn(a0, a1), inter);
+        const float iou = __fdiv_rn(inter, uni);
+        if (mode == FVTG_NMS_NORMAL) {
+          if (iou >= thd) sc[h] = 0.f;  // NaN compares false: kept
+        } else {
+          sc[h] = __fmul_rn(sc[h], __fsub_rn(1.f, iou));
+        }
       }
     }
-    __syncwarp();
   }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (pos[h] != 0xFFFFFFFFu) { S.st[pos[h]] = st[h]; S.ed[pos[h]] = ed[h]; S.sc[pos[h]] = sc[h]; S.src[pos[h]] = sr[h]; }
+  __syncwarp();
   // final descending sort, stable by current position (rank by counting)
   for (int r = lane; r < n; r += 32) {
     const float s = S.sc[r];
@@ -202,8 +215,10 @@ __global__ void __launch_bounds__(DEC_THREADS)
 decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const int npow2,
                   const float* __restrict__ cls, const float* __restrict__ conf,
                   const float* __restrict__ coord, const int* __restrict__ vlen,
-                  const float* __restrict__ duration, const FvtgDecodeOut out) {
+                  const float* __restrict__ duration, const FvtgDecodeOut out, long long* trace) {
+#define DEC_TRACE(ev) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[2048 + (ev)] = clock64(); } while (0)
   extern __shared__ __align__(16) uint8_t dec_smem[];
+  DEC_TRACE(0);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(dec_smem);
   NmsSmem& S = *reinterpret_cast<NmsSmem*>(dec_smem + static_cast<size_t>(npow2) * 8);
   HullSmem& H = *reinterpret_cast<HullSmem*>(dec_smem + static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES);
@@ -230,6 +245,7 @@ decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const
     keys[n] = key;
   }
   __syncthreads();
+  DEC_TRACE(1);
   // bitonic sort, descending
   for (int k = 2; k <= npow2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -244,6 +260,7 @@ decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const
       __syncthreads();
     }
   }
+  DEC_TRACE(2);
   const int topk = p.topk;
   const int top = N < topk ? N : topk;
   const float dur = duration ? duration[b] : 3.0e38f;
@@ -291,12 +308,14 @@ decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const
   }
   if (tid == 0 && out.count) out.count[b] = top;
   __syncthreads();
+  DEC_TRACE(3);
   if (p.nms_mode != FVTG_NMS_NONE && tid < 32) {
     run_nms_and_store(S, H, top, p.nms_mode, p.nms_thd, p.max_after_nms, topk,
                       out.nms_windows ? out.nms_windows + static_cast<size_t>(b) * topk * 3 : nullptr,
                       out.nms_order ? out.nms_order + static_cast<size_t>(b) * topk : nullptr,
                       out.nms_count ? out.nms_count + b : nullptr, tid);
   }
+  DEC_TRACE(4);
 }
 
 __global__ void __launch_bounds__(32)
@@ -373,7 +392,7 @@ int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv,
   const size_t smem = static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES + sizeof(HullSmem);
   ProfScope prof(st, PC_DECODE);
   decode_nms_kernel<<<B, DEC_THREADS, smem, st>>>(p, Lv, n_max, npow2, cls, conf, coord, vlen,
-                                                   duration, out);
+                                                   duration, out, dbg_trace());
   FVTG_LAUNCH_CHECK("decode_nms_kernel");
   return FVTG_OK;
 }

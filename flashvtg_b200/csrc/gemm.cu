@@ -160,6 +160,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_tiles = m_tiles * n_tiles;
   const int total_kb = g.ntaps * g.kb_per_tap;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmA2);
@@ -194,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (e.mode == EPI_DOT)
       for (int i = t; i < 128; i += 256) s_dotw[i] = e.dotw[i];
   }
+  pdl_wait();   // everything above touched only constants / on-chip state
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -495,7 +497,7 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
   const int tiles = m_tiles * (args.N / args.BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(st, PC_GEMM);
-  gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, ta2, tb, to, args);
+  FVTG_CUDA_OK(launch_pdl(gemm_kernel, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, st, ta, ta2, tb, to, args));
   FVTG_LAUNCH_CHECK("gemm_kernel");
   return FVTG_OK;
 }

@@ -93,6 +93,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const int ntiles = (g.M + 127) >> 7;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmWo);
@@ -128,6 +129,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     s_be2[i] = g.be2[i];
   }
   for (int i = threadIdx.x; i < 1024; i += LK_THREADS) s_b1[i] = g.b1[i];
+  pdl_wait();   // everything above touched only constants / on-chip state
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -547,7 +549,7 @@ int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w
     }
   }
   ProfScope prof(st, PC_LAYER);
-  layer_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, st>>>(ta, two, tw1, tw2, a2);
+  FVTG_CUDA_OK(launch_pdl(layer_kernel, dim3(grid), dim3(LK_THREADS), LK_SMEM_BYTES, st, ta, two, tw1, tw2, a2));
   FVTG_LAUNCH_CHECK("layer_kernel");
   return FVTG_OK;
 }

@@ -419,3 +419,15 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 }  // namespace fvtg
+
+namespace fvtg {
+// --------------------------------------- programmatic dependent launch (PDL) --
+// launch_dependents: the next kernel of the stream (launched with the PDL attribute) may start
+// its CTAs as soon as every CTA of this grid has executed this (or exited) and resources free up.
+// wait: blocks until all prerequisite grids have completed and their memory is visible; a no-op
+// when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+}  // namespace fvtg

@@ -49,10 +49,16 @@ sal_matvec_kernel(const float* __restrict__ G, const float* __restrict__ w1,
   float u[SAL_VPB];
 #pragma unroll
   for (int v = 0; v < SAL_VPB; ++v) u[v] = 0.f;
-  for (int k = 0; k < 256; ++k) {  // u[n] = b2[n] + sum_k W2t[k][n] g[k]
-    const float w = __ldg(w2t + k * 256 + c);
+  // u[n] = b2[n] + sum_k W2t[k][n] g[k]: 8 independent weight loads in flight per thread
+  for (int k0 = 0; k0 < 256; k0 += 8) {
+    float w[8];
 #pragma unroll
-    for (int v = 0; v < SAL_VPB; ++v) u[v] += w * s_g[v][k];
+    for (int j = 0; j < 8; ++j) w[j] = __ldg(w2t + (k0 + j) * 256 + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int v = 0; v < SAL_VPB; ++v) u[v] += w[j] * s_g[v][k0 + j];
+    }
   }
   const float bb2 = b2[c], bb1 = b1[c];
 #pragma unroll
@@ -66,10 +72,15 @@ sal_matvec_kernel(const float* __restrict__ G, const float* __restrict__ w1,
   float wv[SAL_VPB];
 #pragma unroll
   for (int v = 0; v < SAL_VPB; ++v) wv[v] = 0.f;
-  for (int n = 0; n < 256; ++n) {  // wv[k] = sum_n W1[n][k] u[n]
-    const float x = __ldg(w1 + n * 256 + c);
+  for (int n0 = 0; n0 < 256; n0 += 8) {  // wv[k] = sum_n W1[n][k] u[n]
+    float x[8];
 #pragma unroll
-    for (int v = 0; v < SAL_VPB; ++v) wv[v] += x * s_u[v][n];
+    for (int j = 0; j < 8; ++j) x[j] = __ldg(w1 + (n0 + j) * 256 + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int v = 0; v < SAL_VPB; ++v) wv[v] += x[j] * s_u[v][n0 + j];
+    }
   }
 #pragma unroll
   for (int v = 0; v < SAL_VPB; ++v) {

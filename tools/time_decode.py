@@ -30,3 +30,13 @@ for mode in (None, "normal", "linear", "hull"):
     e1.record()
     torch.cuda.synchronize()
     print(mode, f"{e0.elapsed_time(e1) * 100:.1f} us per call (incl. output allocation)")
+
+from flashvtg_b200 import _lib
+lib = _lib.load()
+buf = torch.zeros(4096, dtype=torch.int64, device=dev)
+lib.fvtg_dbg_set_trace(buf.data_ptr())
+m.decode(cls, conf, coord, vlen, 75, nms="normal")
+torch.cuda.synchronize()
+lib.fvtg_dbg_set_trace(None)
+t = buf.cpu()[2048:2053].tolist()
+print("decode CTA 0 cycles: keys %d, sort %d, decode+compose %d, nms %d" % (t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3]))
