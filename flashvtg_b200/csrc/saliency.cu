@@ -32,14 +32,14 @@ sal_colmean_kernel(const float* __restrict__ F, const int* __restrict__ vlen, fl
   }
 }
 
-constexpr int SAL_VPB = 8;
+constexpr int SAL_VPB = 2;  // few videos per CTA: the weight-load latency chain is hidden by 4+ co-resident CTAs per SM
 
 __global__ void __launch_bounds__(256)
 sal_matvec_kernel(const float* __restrict__ G, const float* __restrict__ w1,
                   const float* __restrict__ b1, const float* __restrict__ w2t,
                   const float* __restrict__ b2, float* __restrict__ WV, float* __restrict__ Cc, int B) {
-  __shared__ float s_g[SAL_VPB][256];
-  __shared__ float s_u[SAL_VPB][256];
+  __shared__ __align__(16) float s_g[SAL_VPB][256];
+  __shared__ __align__(16) float s_u[SAL_VPB][256];
   __shared__ float s_red[SAL_VPB][8];
   const int c = threadIdx.x, warp = c >> 5, lane = c & 31;
   const int b0 = blockIdx.x * SAL_VPB;
@@ -49,15 +49,19 @@ sal_matvec_kernel(const float* __restrict__ G, const float* __restrict__ w1,
   float u[SAL_VPB];
 #pragma unroll
   for (int v = 0; v < SAL_VPB; ++v) u[v] = 0.f;
-  // u[n] = b2[n] + sum_k W2t[k][n] g[k]: 8 independent weight loads in flight per thread
+  // u[n] = b2[n] + sum_k W2t[k][n] g[k]: 8 independent weight loads in flight per thread, the
+  // videos' g values come as 16-byte broadcast loads (4 k per LDS)
   for (int k0 = 0; k0 < 256; k0 += 8) {
     float w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = __ldg(w2t + (k0 + j) * 256 + c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int v = 0; v < SAL_VPB; ++v) u[v] += w[j] * s_g[v][k0 + j];
+    for (int v = 0; v < SAL_VPB; ++v) {
+      const float4 ga = *reinterpret_cast<const float4*>(&s_g[v][k0]);
+      const float4 gb = *reinterpret_cast<const float4*>(&s_g[v][k0 + 4]);
+      // same summation order as a plain k loop (bit-identical to the scalar version)
+      u[v] += w[0] * ga.x; u[v] += w[1] * ga.y; u[v] += w[2] * ga.z; u[v] += w[3] * ga.w;
+      u[v] += w[4] * gb.x; u[v] += w[5] * gb.y; u[v] += w[6] * gb.z; u[v] += w[7] * gb.w;
     }
   }
   const float bb2 = b2[c], bb1 = b1[c];
@@ -77,9 +81,11 @@ sal_matvec_kernel(const float* __restrict__ G, const float* __restrict__ w1,
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __ldg(w1 + (n0 + j) * 256 + c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int v = 0; v < SAL_VPB; ++v) wv[v] += x[j] * s_u[v][n0 + j];
+    for (int v = 0; v < SAL_VPB; ++v) {
+      const float4 ua = *reinterpret_cast<const float4*>(&s_u[v][n0]);
+      const float4 ub = *reinterpret_cast<const float4*>(&s_u[v][n0 + 4]);
+      wv[v] += x[0] * ua.x; wv[v] += x[1] * ua.y; wv[v] += x[2] * ua.z; wv[v] += x[3] * ua.w;
+      wv[v] += x[4] * ub.x; wv[v] += x[5] * ub.y; wv[v] += x[6] * ub.z; wv[v] += x[7] * ub.w;
     }
   }
 #pragma unroll
