@@ -100,6 +100,17 @@ class FvtgDecodeOut(C.Structure):
                 ("count", vp), ("nms_count", vp)]
 
 
+RAW_MAX_GROUPS = 4
+RAW_F32, RAW_F16, RAW_BF16 = 0, 1, 2
+
+
+class FvtgRawBatch(C.Structure):
+    _fields_ = [("B", i32), ("Lv", i32), ("Lt", i32), ("n_groups", i32),
+                ("group_dim", i32 * RAW_MAX_GROUPS), ("t_dim", i32), ("dtype", i32),
+                ("normalize_v", i32), ("normalize_t", i32), ("use_tef", i32), ("_pad", i32),
+                ("vid", vp * RAW_MAX_GROUPS), ("txt", vp), ("vid_len", vp), ("txt_len", vp)]
+
+
 # name -> (restype, argtypes); also the list the ABI test checks against the header.
 SIGNATURES = {
     "fvtg_workspace_bytes": (C.c_size_t, [C.POINTER(FvtgCfg), i32, i32, i32]),
@@ -115,6 +126,7 @@ SIGNATURES = {
     "fvtg_forward": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgWeights), C.POINTER(FvtgBatch), vp,
                            C.POINTER(FvtgDecodeParams), C.POINTER(FvtgFusionOut),
                            C.POINTER(FvtgHeadsOut), C.POINTER(FvtgDecodeOut), vp, C.c_size_t, vp]),
+    "fvtg_prepare_inputs": (i32, [C.POINTER(FvtgRawBatch), vp, vp, vp, vp, vp]),
     "fvtg_last_launch_count": (C.c_int64, []),
     "fvtg_last_error": (C.c_char_p, []),
     "fvtg_abi_version": (i32, []),

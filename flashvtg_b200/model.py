@@ -257,6 +257,90 @@ class FlashVTGB200(torch.nn.Module):
         out["launches"] = sum(r.launches for _, _, r in pending)
         return out
 
+    @torch.no_grad()
+    def infer_raw_host(self, raw_vid, vid_len: torch.Tensor, raw_txt: torch.Tensor, txt_len: torch.Tensor,
+                       duration: Optional[torch.Tensor] = None, nms: Optional[str] = "normal",
+                       nms_thd: Optional[float] = None, device: Optional[torch.device] = None,
+                       chunk_videos: int = 128, normalize_v: bool = True, normalize_t: bool = True,
+                       use_tef: bool = True, out: Optional[dict] = None) -> dict:
+        """Like infer_host, but from RAW feature arrays as they sit in the feature files (one HOST tensor
+        (B, Lv, D_g) per video feature directory + the raw text features, fp32 / fp16 / bf16): the loader's
+        per-item work (L2 normalisation per directory, concatenation, TEF, padding) runs on the device
+        (flashvtg_b200.inputs.prepare_inputs), so half-precision feature stores cross PCIe at half the bytes.
+        Replaces StartEndDataset._load_model_inputs + start_end_collate + prepare_batch_inputs + forward."""
+        from .inputs import prepare_inputs
+        cfg = self.cfg
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        raw_vid = list(raw_vid)
+        B, Lv = raw_vid[0].shape[0], raw_vid[0].shape[1]
+        Lt = raw_txt.shape[1]
+        if duration is None:
+            duration = vid_len.to(torch.float32) * cfg.clip_length
+        topk = cfg.max_num_moment
+        do_nms = _NMS_MODES[nms] != _lib.NMS_NONE
+        if out is None:
+            def pin(*shape, dtype=torch.float32):
+                return torch.empty(*shape, dtype=dtype).pin_memory()
+            out = {"boundary": pin(B, topk, 3), "windows": pin(B, topk, 3),
+                   "count": pin(B, dtype=torch.int32), "saliency": pin(B, Lv), "t2vattn": pin(B, Lv)}
+            if do_nms:
+                out.update({"nms_windows": pin(B, topk, 3), "nms_order": pin(B, topk, dtype=torch.int32),
+                            "nms_count": pin(B, dtype=torch.int32)})
+        launches = 0
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            key = (dev.index, "copy_stream")
+            if key not in self._ws:
+                self._ws[key] = torch.cuda.Stream(device=dev)
+            cp = self._ws[key]
+            cb = max(1, min(chunk_videos, B))
+            skey = (dev.index, "raw_slots", cb, Lv, Lt, raw_txt.dtype, tuple(g.shape[2] for g in raw_vid),
+                    raw_txt.shape[2])
+            if skey not in self._ws:
+                def slot():
+                    return {"vid": [torch.empty(cb, Lv, g.shape[2], dtype=g.dtype, device=dev) for g in raw_vid],
+                            "txt": torch.empty(cb, Lt, raw_txt.shape[2], dtype=raw_txt.dtype, device=dev),
+                            "vid_len": torch.empty(cb, dtype=torch.int32, device=dev),
+                            "txt_len": torch.empty(cb, dtype=torch.int32, device=dev),
+                            "duration": torch.empty(cb, dtype=torch.float32, device=dev)}
+                self._ws[skey] = (slot(), slot())
+            slots = self._ws[skey]
+            free_ev = [None, None]
+            cp.wait_stream(cur)
+            for i, b0 in enumerate(range(0, B, cb)):
+                nb = min(cb, B - b0)
+                sl = slots[i & 1]
+                with torch.cuda.stream(cp):
+                    if free_ev[i & 1] is not None:
+                        cp.wait_event(free_ev[i & 1])
+                    for dst, src in zip(sl["vid"], raw_vid):
+                        dst[:nb].copy_(src[b0:b0 + nb], non_blocking=True)
+                    sl["txt"][:nb].copy_(raw_txt[b0:b0 + nb], non_blocking=True)
+                    sl["vid_len"][:nb].copy_(vid_len[b0:b0 + nb], non_blocking=True)
+                    sl["txt_len"][:nb].copy_(txt_len[b0:b0 + nb], non_blocking=True)
+                    sl["duration"][:nb].copy_(duration[b0:b0 + nb], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(cp)
+                cur.wait_event(ready)
+                sv, _, st, _ = prepare_inputs([g[:nb] for g in sl["vid"]], sl["vid_len"][:nb], sl["txt"][:nb],
+                                              sl["txt_len"][:nb], normalize_v, normalize_t, use_tef,
+                                              want_masks=False)
+                hv = vid_len[b0:b0 + nb]
+                r = self.infer(sv, sl["vid_len"][:nb], st, sl["txt_len"][:nb], duration=sl["duration"][:nb],
+                               nms=nms, nms_thd=nms_thd, uniform_len=bool((hv == hv[0]).all()))
+                free_ev[i & 1] = torch.cuda.Event()
+                free_ev[i & 1].record(cur)
+                launches += r.launches + 2
+                for name, t in (("boundary", r.boundary), ("windows", r.windows), ("count", r.count),
+                                ("saliency", r.saliency), ("t2vattn", r.t2vattn),
+                                ("nms_windows", r.nms_windows), ("nms_order", r.nms_order),
+                                ("nms_count", r.nms_count)):
+                    if t is not None and name in out:
+                        out[name][b0:b0 + nb].copy_(t, non_blocking=True)
+            cur.synchronize()
+        out["launches"] = launches
+        return out
+
     def _host_slots(self, dev: torch.device, cb: int, Lv: int, Lt: int):
         key = (dev.index, "host_slots", cb, Lv, Lt)
         if key not in self._ws:

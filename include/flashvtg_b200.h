@@ -227,6 +227,33 @@ int32_t fvtg_forward(const FvtgCfg* cfg, const FvtgWeights* w, const FvtgBatch* 
                      const FvtgHeadsOut* hout, const FvtgDecodeOut* dout, void* workspace,
                      size_t ws_bytes, void* stream);
 
+/* ---- Device-resident input pipeline (what the reference's loader does per item on the host) ----
+ * Replaces, for raw feature rows already on the device: l2_normalize_np_array per feature directory
+ * (FlashVTG/start_end_dataset.py:524-530, utils/basic_utils.py:84-86), concatenation, the temporal
+ * endpoint features (start_end_dataset.py:174-180), zero padding and the 0/1 masks of start_end_collate
+ * (utils/tensor_utils.py:5-53).  Raw rows may be fp32 / fp16 / bf16 (the loader's astype(np.float32)). */
+#define FVTG_RAW_MAX_GROUPS 4
+#define FVTG_RAW_F32 0
+#define FVTG_RAW_F16 1
+#define FVTG_RAW_BF16 2
+typedef struct FvtgRawBatch {
+  int32_t B, Lv, Lt;
+  int32_t n_groups;                         /* feature directories of the video (--v_feat_dirs) */
+  int32_t group_dim[FVTG_RAW_MAX_GROUPS];   /* their feature dims, concatenated in this order */
+  int32_t t_dim;                            /* raw text feature dim */
+  int32_t dtype;                            /* FVTG_RAW_* of every raw array */
+  int32_t normalize_v, normalize_t;         /* not --no_norm_vfeat / --no_norm_tfeat */
+  int32_t use_tef;                          /* --ctx_mode contains "tef": append [i/L, (i+1)/L] */
+  int32_t _pad;
+  const void* vid[FVTG_RAW_MAX_GROUPS];     /* [B][Lv][group_dim[g]], rows >= vid_len[b] ignored */
+  const void* txt;                          /* [B][Lt][t_dim] */
+  const int32_t* vid_len;                   /* [B] */
+  const int32_t* txt_len;                   /* [B] */
+} FvtgRawBatch;
+/* src_vid fp32 [B][Lv][sum(group_dim) + 2*use_tef], src_txt fp32 [B][Lt][t_dim]; masks fp32 [B][L] or null. */
+int32_t fvtg_prepare_inputs(const FvtgRawBatch* raw, float* src_vid, float* src_vid_mask,
+                            float* src_txt, float* src_txt_mask, void* stream);
+
 /* Number of kernel launches the last fvtg_* compute call on this thread issued. */
 int64_t fvtg_last_launch_count(void);
 const char* fvtg_last_error(void);

@@ -180,9 +180,34 @@ def make_postproc():
     print("wrote postproc_cases.json", len(out))
 
 
+def make_inputs_golden():
+    """tests/golden/inputs_case.npz: the reference loader's own functions (l2_normalize_np_array,
+    the TEF expression of start_end_dataset.py:175-177, pad_sequences_1d) on tests/test_inputs._raw_case."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_inputs import _raw_case
+    sys.path.insert(0, "/root/reference")
+    from utils.basic_utils import l2_normalize_np_array
+    from utils.tensor_utils import pad_sequences_1d
+    groups, txt, vlen, tlen = _raw_case()
+    vs, qs = [], []
+    for b in range(len(vlen)):
+        fl = [l2_normalize_np_array(g[b, :vlen[b]].astype(np.float32)) for g in groups]
+        v = torch.from_numpy(np.concatenate(fl, axis=1))
+        L = len(v)
+        tef_st = torch.arange(0, L, 1.0) / L
+        tef_ed = tef_st + 1.0 / L
+        vs.append(torch.cat([v, torch.stack([tef_st, tef_ed], dim=1)], dim=1))
+        qs.append(torch.from_numpy(l2_normalize_np_array(txt[b, :tlen[b]].astype(np.float32))))
+    pv, mv = pad_sequences_1d(vs, dtype=torch.float32, fixed_length=None)
+    pq, mq = pad_sequences_1d(qs, dtype=torch.float32, fixed_length=None)
+    np.savez_compressed(os.path.join(OUT, "inputs_case.npz"), src_vid=pv.numpy(), vid_mask=mv.numpy(),
+                        src_txt=pq.numpy(), txt_mask=mq.numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     assert ref_loader.available(), "needs /root/reference"
     make_nms()
     make_postproc()
     make_forward()
+    make_inputs_golden()

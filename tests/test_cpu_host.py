@@ -45,7 +45,9 @@ def test_ctypes_structs_match_the_c_header():
                "FvtgScoreHead": ["conv", "mlp", "last_w", "last_b"],
                "FvtgWeights": ["vid", "txt", "dummy_tok", "dummy", "t2v", "enc", "sal_w1", "pyr",
                                "cls", "conf", "coord1", "coord2", "coef", "x"],
-               "FvtgBatch": ["B", "Lv", "Lt", "vid", "txt", "vid_len", "txt_len"],
+               "FvtgBatch": ["B", "Lv", "Lt", "uniform_vid_len", "vid", "txt", "vid_len", "txt_len"],
+               "FvtgRawBatch": ["B", "Lv", "Lt", "n_groups", "group_dim", "t_dim", "dtype", "normalize_v",
+                                "normalize_t", "use_tef", "vid", "txt", "vid_len", "txt_len"],
                "FvtgFusionOut": ["video_emb", "saliency", "t2v", "dummy_tokens"],
                "FvtgHeadsOut": ["n_max", "cls_logit", "conf_logit", "coord"],
                "FvtgDecodeParams": ["nms_thd", "x", "clip_len", "inv_clip_len", "min_ts", "max_ts",
