@@ -293,7 +293,7 @@ def run_ours(args):
 
         def step_raw():
             o = model.infer_raw_host(raw_v, host["vid_len"], raw_t, host["txt_len"], duration=host["duration"],
-                                     nms="normal", device=dev, chunk_videos=args.e2e_chunk, out=raw_out.get("o"))
+                                     nms="normal", device=dev, chunk_videos=args.raw_chunk, out=raw_out.get("o"))
             raw_out["o"] = o
         for _ in range(2):
             step_raw()
@@ -311,6 +311,7 @@ def run_ours(args):
         raw = {"value": world * B * k2 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k2,
                "h2d_bytes_per_step": world * int(sum(v.numel() * v.element_size() for v in raw_v) +
                                                  raw_t.numel() * raw_t.element_size()),
+               "chunk_videos": args.raw_chunk,
                "api": "FlashVTGB200.infer_raw_host: raw fp16 feature arrays -> device L2-norm + TEF + padding "
                       "(fvtg_prepare_inputs) -> forward -> host spans"}
         e2e["raw_fp16_features"] = raw
@@ -398,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raw-leg", action="store_true", help="skip the informational raw-fp16-feature e2e leg")
+    ap.add_argument("--raw-chunk", type=int, default=256, help="videos per chunk of the raw-feature leg")
     ap.add_argument("--e2e-chunk", type=int, default=128, help="videos per pipelined H2D/compute chunk")
     ap.add_argument("--kernel-only", action="store_true",
                     help="device-resident timing only (for runs under ncu): no e2e / roofline / CPU legs")

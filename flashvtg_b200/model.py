@@ -261,7 +261,7 @@ class FlashVTGB200(torch.nn.Module):
     def infer_raw_host(self, raw_vid, vid_len: torch.Tensor, raw_txt: torch.Tensor, txt_len: torch.Tensor,
                        duration: Optional[torch.Tensor] = None, nms: Optional[str] = "normal",
                        nms_thd: Optional[float] = None, device: Optional[torch.device] = None,
-                       chunk_videos: int = 128, normalize_v: bool = True, normalize_t: bool = True,
+                       chunk_videos: int = 256, normalize_v: bool = True, normalize_t: bool = True,
                        use_tef: bool = True, out: Optional[dict] = None) -> dict:
         """Like infer_host, but from RAW feature arrays as they sit in the feature files (one HOST tensor
         (B, Lv, D_g) per video feature directory + the raw text features, fp32 / fp16 / bf16): the loader's
