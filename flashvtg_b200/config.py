@@ -121,6 +121,16 @@ PRESETS = {
                               t2v_layers=8, strides=(1, 2, 4, 8, 16, 32), kernel_size=5,
                               num_conv_layers=2, num_mlp_layers=5, clip_length=2.0, max_q_l=100,
                               dset_name="tacos", name="tacos_deep"),
+    # highlight detection (data/HD.py: a single pyramid level, buffer 2048)
+    # scripts/tvsum/train.sh:23-56: SlowFast+CLIP 2816+2 TEF, CLIP text, 3 dummies, t2v 2, k5/c2/m3
+    "tvsum": ModelConfig(v_feat_dim=2818, t_feat_dim=512, num_dummies=3, dummy_layers=2, t2v_layers=2,
+                         enc_layers=3, strides=(1,), kernel_size=5, num_conv_layers=2, num_mlp_layers=3,
+                         clip_length=2.0, buffer_size=2048, max_q_l=100, dset_name="tvsum", name="tvsum"),
+    # scripts/youtube_uni/train.sh:20-84: same features, 1 dummy, clip_length 1
+    "youtube_uni": ModelConfig(v_feat_dim=2818, t_feat_dim=512, num_dummies=1, dummy_layers=2, t2v_layers=2,
+                               enc_layers=3, strides=(1,), kernel_size=5, num_conv_layers=2,
+                               num_mlp_layers=3, clip_length=1.0, buffer_size=2048, max_q_l=100,
+                               dset_name="youtube_uni", name="youtube_uni"),
 }
 
 

@@ -141,3 +141,54 @@ def compute_mr_results(model, eval_loader, opt=None, nms: Optional[str] = None):
                                pred_relevant_windows=w.tolist(),
                                pred_saliency_scores=round4_host(sal[i, : vl[i]]).tolist()))
     return mr_res
+
+
+def highlight_ap(pred, label, topk: Optional[int] = None) -> float:
+    """Average precision of one ranked binary relevance list as FlashVTG/inference.py:169-186,191-213
+    computes it (trapezoidal precision-recall area, UMT convention): `pred` scores (n,), `label` 0/1 (n,);
+    the list is ranked by score (descending) and cut to `topk` (5 for TVSum, None for YouTube-HL)."""
+    pred = np.asarray(pred, dtype=np.float64)
+    label = np.asarray(label, dtype=np.float64)
+    order = np.argsort(-pred, kind="stable")
+    rel = label[order][:topk] if topk is not None else label[order]
+    num_gt = rel.sum()
+    if num_gt == 0:
+        return 0.0
+    hits = np.cumsum(rel)
+    rec = hits / num_gt
+    prc = hits / np.arange(1, len(rel) + 1)
+    rec_prev = np.concatenate([[0.0], rec[:-1]])
+    prc_prev = np.concatenate([[1.0], prc[:-1]])
+    return float(np.sum((rec - rec_prev) * (prc_prev + prc) / 2))
+
+
+def compute_hl_results(model, eval_loader, opt=None):
+    """Counterpart of compute_hl_results (FlashVTG/inference.py:118-229) for a FlashVTGB200 model: forward
+    (saliency_scores on the device, any batch size), then the per-video top-5 mAP (TVSum: 20 annotators,
+    label binarised at its median) or full-list AP (YouTube-HL).  eval_loader yields (query_meta,
+    batched_inputs) with batched_inputs as prepare_batch_inputs returns them and meta["label"] the raw
+    labels.  Returns dict(mAP=...) like the reference's `submmission`."""
+    dset = getattr(opt, "dset_name", model.cfg.dset_name)
+    if dset not in ("tvsum", "youtube_uni"):
+        raise ValueError("No such dataset")   # inference.py:214-216
+    aps = []
+    for query_meta, inp in eval_loader:
+        vid_len = inp["src_vid_mask"].sum(1).to(torch.int32)
+        txt_len = inp["src_txt_mask"].sum(1).to(torch.int32)
+        r = model.infer(inp["src_vid"].contiguous().float(), vid_len, inp["src_txt"].contiguous().float(),
+                        txt_len, nms=None)
+        sal = r.saliency.cpu().numpy()
+        for i, meta in enumerate(query_meta):
+            label = np.asarray(meta["label"], dtype=np.float64)
+            pred = sal[i, : len(label)]
+            if dset == "tvsum":
+                video_ap = []
+                for a in range(label.shape[1]):
+                    cur = label[:, a]
+                    # torch.median returns the LOWER of the two middle values for even counts
+                    med = np.sort(cur)[(len(cur) - 1) // 2]
+                    video_ap.append(highlight_ap(pred, (cur > med).astype(np.float64), topk=5))
+                aps.append(video_ap)
+            else:
+                aps.append([highlight_ap(pred, label.reshape(-1))])
+    return dict(mAP=round(float(np.mean(aps)), 5)) if aps else dict(mAP=0.0)
