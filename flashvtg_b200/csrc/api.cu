@@ -183,6 +183,7 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
     a.out = w.att;
     a.B = B; a.Lq = Lseq; a.Lk = Lseq;
     a.klen_src = klen_src; a.kbase = kbase; a.v_first = 0; a.tsum = nullptr;
+    a.trace = dbg_trace();
     FVTG_TRY(launch_attention(st, a));
   }
   LayerArgs a = layer_args(L, rows, LAYER_SA, xf);
@@ -211,6 +212,7 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
     a.B = B; a.Lq = Lv; a.Lk = S;
     a.klen_src = tlen; a.kbase = c.num_dummies; a.v_first = c.num_dummies;
     a.tsum = w.tsum + static_cast<size_t>(layer) * 8 * B * Lv;
+    a.trace = dbg_trace();
     FVTG_TRY(launch_attention(st, a));
   }
   LayerArgs a = layer_args(L, rows, LAYER_T2V, w.Yf);

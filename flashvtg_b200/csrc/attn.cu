@@ -178,6 +178,8 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
   const int g = lane >> 2, t = lane & 3;
   pdl_launch_dependents();
   pdl_wait();
+#define AT_TRACE(ev) do { if (a.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 1000)) a.trace[3072 + (blockIdx.x ? 8 : 0) + (ev)] = clock64(); } while (0)
+  AT_TRACE(0);
   int klen = a.kbase + a.klen_src[b];
   if (klen > a.Lk) klen = a.Lk;
   const int col0 = hg * 128;
@@ -206,6 +208,7 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
   }
   cp_async_wait_all();
   __syncthreads();
+  AT_TRACE(1);
 
   const int hl = warp & 3;            // head within the group
   const int h = hg * 4 + hl;
@@ -317,12 +320,15 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
       }
     }
   }
+  AT_TRACE(2);
   __syncthreads();
+  AT_TRACE(3);
   for (int idx = tid; idx < a.Lq * 16; idx += 256) {
     const int r = idx >> 4, c = idx & 15;
     *reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(b) * a.Lq + r) * 256 + col0 + c * 8) =
         *reinterpret_cast<const uint4*>(sQ + r * AV_PITCH + c * 8);
   }
+  AT_TRACE(4);
 }
 
 template <int NT, bool KV_SHARED>

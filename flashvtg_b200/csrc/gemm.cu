@@ -129,7 +129,7 @@ __device__ __forceinline__ void act32(float* v, int act, float slope) {
   }
 }
 
-__device__ __forceinline__ void gemm_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void gemm_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -150,7 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* s_gamma = s_bias + 1024;
   float* s_beta = s_gamma + 256;
   float* s_dotw = s_beta + 256;
-  float2* s_stat = reinterpret_cast<float2*>(s_dotw + 256);  // [2][128]
+  float2* s_stat = reinterpret_cast<float2*>(s_dotw + 256);  // [4 column quarters][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -174,7 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
+      mbar_init(&tempty[a], 16);
     }
     fence_mbar_init();
   }
@@ -185,15 +185,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp >= 4) {
     const GemmEpi& e = g.epi;
     const int t = threadIdx.x - 128;
-    for (int i = t; i < g.N && i < 1024; i += 256) s_bias[i] = e.bias ? e.bias[i] : 0.f;
+    for (int i = t; i < g.N && i < 1024; i += 512) s_bias[i] = e.bias ? e.bias[i] : 0.f;
     if (e.mode == EPI_ROW && e.gamma) {
-      for (int i = t; i < 256; i += 256) {
+      for (int i = t; i < 256; i += 512) {
         s_gamma[i] = e.gamma[i];
         s_beta[i] = e.beta[i];
       }
     }
     if (e.mode == EPI_DOT)
-      for (int i = t; i < 128; i += 256) s_dotw[i] = e.dotw[i];
+      for (int i = t; i < 128; i += 512) s_dotw[i] = e.dotw[i];
   }
   pdl_wait();   // everything above touched only constants / on-chip state
   tc_fence_before();
@@ -260,12 +260,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ----------------------------------------------------------- epilogue --
-    // 8 warps, two threads per accumulator row: TMEM lane quadrant = warp % 4, column half = hf.
+    // 16 warps, four threads per accumulator row: TMEM lane quadrant = warp % 4, column quarter = qt.
     const GemmEpi& e = g.epi;
     const int ew = warp - 4;
-    const int wq = ew & 3, hf = ew >> 2;
+    const int wq = ew & 3, qt = ew >> 2;
     const int r = wq * 32 + lane;
-    const int HC = BN >> 1;  // columns owned by this thread
+    const int QC = BN >> 2;  // columns owned by this thread
     const bool leader = threadIdx.x == 128;
     const float slope = act_slope(e.act, e.prelu);
     // bf16 tile outputs with an identity row map leave through shared memory + TMA (coalesced)
@@ -300,8 +300,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (ln) {
           float s1 = 0.f, s2 = 0.f, shift = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            const int c0 = hf * 128 + c * 32;
+          for (int c = 0; c < 2; ++c) {
+            const int c0 = qt * 64 + c * 32;
             tmem_ld32(tacc + c0, u);
             tmem_ld_wait();
             add_bias32(u, s_bias + c0, v);
@@ -320,20 +320,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tmem_st32(tacc + c0, u);
           }
           tmem_st_wait();
-          s_stat[hf * 128 + r] = make_float2(shift + s1 * (1.f / 128.f), s2 - s1 * s1 * (1.f / 128.f));
+          // per-quarter partial (mean of 64, centred sum of squares of 64), combined over the 4 quarters
+          s_stat[qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
           gemm_epi_bar();
-          const float2 a = s_stat[r], b2 = s_stat[128 + r];
-          const float dm = a.x - b2.x;
-          mean = 0.5f * (a.x + b2.x);
-          const float var = fmaxf((a.y + b2.y + dm * dm * 64.f) * (1.f / 256.f), 0.f);
-          rstd = rsqrtf(var + 1e-5f);
+          const float2 a0 = s_stat[r], a1 = s_stat[128 + r], a2 = s_stat[256 + r], a3 = s_stat[384 + r];
+          mean = 0.25f * (a0.x + a1.x + a2.x + a3.x);
+          const float d0 = a0.x - mean, d1 = a1.x - mean, d2 = a2.x - mean, d3 = a3.x - mean;
+          const float m2 = a0.y + a1.y + a2.y + a3.y + 64.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+          rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
         }
         int prow = row;
         if (e.pos_mod > 0) prow = row % e.pos_mod;
         const bool st_pos = e.out_bf16_pos && ri.inb && (e.pos_rowlim <= 0 || prow < e.pos_rowlim);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int c0 = hf * 128 + c * 32;
+        for (int c = 0; c < 2; ++c) {
+          const int c0 = qt * 64 + c * 32;
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
           if (ln) {
@@ -386,7 +387,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if (e.mode == EPI_TILE) {
         // lean inner loops: 16-byte bias loads, the activation switch hoisted out of the element loop
-        for (int c0 = hf * HC; c0 < (hf + 1) * HC; c0 += 32) {
+        for (int c0 = qt * QC; c0 < (qt + 1) * QC; c0 += 32) {
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
           add_bias32(u, s_bias + n0 + c0, v);
@@ -399,7 +400,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if (e.mode == EPI_DOT) {
         float dot = 0.f;
-        for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
+        {
+          const int c0 = qt * 32;   // BN == 128: 32 columns per thread
           tmem_ld32(tacc + c0, u);
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
@@ -413,13 +415,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             dot += fmaxf(__uint_as_float(u[4 * i + 3]) + b.w, 0.f) * w.w;
           }
         }
-        if (hf == 1) s_stat[r].x = dot;
+        if (qt > 0) s_stat[qt * 128 + r].x = dot;
         gemm_epi_bar();
-        if (hf == 0 && ri.valid)
-          e.out_dot[static_cast<size_t>(ri.b) * e.geo.n_max + ri.n] = dot + s_stat[r].x + e.dotb;
+        if (qt == 0 && ri.valid)
+          e.out_dot[static_cast<size_t>(ri.b) * e.geo.n_max + ri.n] =
+              ((dot + s_stat[128 + r].x) + (s_stat[256 + r].x + s_stat[384 + r].x)) + e.dotb;
         gemm_epi_bar();  // s_stat is rewritten by the next tile
       } else {  // EPI_COORD
-        if (hf == 0) {
+        if (qt == 0) {
           tmem_ld16(tacc, u);
           tmem_ld_wait();
           if (ri.valid) {

@@ -5,7 +5,7 @@
 //   warp 0      TMA producer   (A / W tiles -> 3-stage SWIZZLE_128B smem ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, 128 x BN x 16)
 //   warp 2      TMEM allocator (512 columns = two BN<=256 accumulators, double buffered)
-//   warps 4..11 epilogue       (two threads per row; tcgen05.ld -> bias / activation / residual /
+//   warps 4..19 epilogue       (four threads per row; tcgen05.ld -> bias / activation / residual /
 //                               LayerNorm / row-dot / exp; bf16 tiles leave through a swizzled
 //                               staging tile + TMA store), overlapping the next tile's MMAs
 //
@@ -23,7 +23,7 @@ namespace fvtg {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 3;
-constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_THREADS = 640;       // 4 control warps + 16 epilogue warps
 constexpr int GEMM_MAX_TAPS = 8;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB
 constexpr int GEMM_B_BYTES_MAX = 256 * GEMM_BK * 2;        // 32 KB
@@ -31,7 +31,7 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES_MAX;
 constexpr int GEMM_OUT_BYTES = 4 * GEMM_A_BYTES;           // staging tile for TMA stores: 128 x 256 bf16
 constexpr int GEMM_PARAM_FLOATS = 1024 + 256 + 256 + 256;  // bias, gamma, beta, dotw
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_OUT_BYTES + 256 +
-                                GEMM_PARAM_FLOATS * 4 + 2 * 128 * 8 /*LN stats*/ + 1024 /*align slack*/;
+                                GEMM_PARAM_FLOATS * 4 + 4 * 128 * 8 /*LN stats*/ + 1024 /*align slack*/;
 static_assert(GEMM_SMEM_BYTES <= 232448, "gemm kernel shared memory over the 227 KB limit");
 
 enum EpiMode { EPI_ROW = 0, EPI_TILE = 1, EPI_DOT = 2, EPI_COORD = 3 };

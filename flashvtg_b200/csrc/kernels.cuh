@@ -61,6 +61,7 @@ struct AttnArgs {
   int kbase;
   int v_first;              // keys < v_first contribute no value (the dummy tokens, crossattention.py:385-386)
   float* tsum;              // optional fp32 [8][B*Lq] (this layer's slot): probability mass on keys >= v_first
+  long long* trace;         // debug: clock64 stamps of CTA 0 / CTA 1000 at +3072 (fvtg_dbg_set_trace)
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
 
