@@ -339,11 +339,12 @@ def run_ours(args):
         fl = flops_by_kernel_class(cfg, LV, LT)
         names = {"layer": "layer_kernel (tcgen05/TMEM + TMA: out_proj + LN1 + FFN + LN2 fused)",
                  "gemm": "gemm_kernel (persistent tcgen05/TMEM + TMA GEMM, fused epilogues)",
-                 "attention": "attention_kernel (per video x 4-head group, mma.sync)"}
+                 "attention": "attention_kernel (per video x 4-head group, mma.sync)",
+                 "inproj": "inproj_kernel (LayerNorm-folded first projection, fp32 features read once, tcgen05)"}
         cls_ms = {n: ms_c[i] / ksteps for i, n in enumerate(_lib.PROF_CLASSES)}
         cls_ln = {n: int(ln_c[i] // ksteps) for i, n in enumerate(_lib.PROF_CLASSES)}
         per_kernel = {}
-        for n in ("layer", "gemm", "attention"):
+        for n in ("layer", "gemm", "attention", "inproj"):
             if cls_ms[n] > 0:
                 a = fl[n] * B / (cls_ms[n] * 1e-3) / 1e12
                 per_kernel[n] = {"kernel": names[n], "achieved_tflops": a, "frac": a / peak,

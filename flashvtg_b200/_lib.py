@@ -12,13 +12,13 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libflashvtg_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 8
 MAX_LEVELS = 8
 MAX_CONVS = 4
 MAX_MLP = 8
 MAX_TOPK = 64
-PROF_CLASSES = ("gemm", "attention", "ln_cast", "decode_nms", "other", "layer")
+PROF_CLASSES = ("gemm", "attention", "inproj", "decode_nms", "other", "layer")
 
 NMS_NONE, NMS_NORMAL, NMS_LINEAR, NMS_HULL = -1, 0, 1, 2
 
@@ -43,7 +43,8 @@ class FvtgLinear(C.Structure):
 
 
 class FvtgInProj(C.Structure):
-    _fields_ = [("ln0", FvtgLN), ("fc0", FvtgLinear), ("ln1", FvtgLN), ("fc1", FvtgLinear)]
+    _fields_ = [("ln0", FvtgLN), ("fc0", FvtgLinear), ("ln1", FvtgLN), ("fc1", FvtgLinear),
+                ("fc0_wsum", vp)]
 
 
 class FvtgEncLayer(C.Structure):

@@ -178,7 +178,8 @@ def flops_by_kernel_class(cfg: ModelConfig, lv: int, lt: int) -> dict:
     """Algorithmic FLOPs (2 x MAC, unpadded dims) of one video split by the kernel class that
     computes them (bench.py roofline numerators; classes as in fvtg_prof_collect):
       layer     - fused layer-tail kernel: out_proj + FFN of every dummy / T2V / encoder layer
-      gemm      - persistent tcgen05 GEMM: input projections, QKV in-projections, pyramid convs, heads
+      inproj    - first input-projection layer with its LayerNorm folded in (reads the fp32 features once)
+      gemm      - persistent tcgen05 GEMM: second projections, QKV in-projections, pyramid convs, heads
       attention - per-(video, head) QK^T and PV products (legacy mma.sync kernel)
     The saliency mat-vecs (9.9 MFLOP at QVH-IV2) are left out, as in gemm_flops_per_video."""
     d, ff, dh, H = 256, 1024, 32, 8
@@ -189,4 +190,6 @@ def flops_by_kernel_class(cfg: ModelConfig, lv: int, lt: int) -> dict:
     attn = cfg.dummy_layers * H * (2 * s * s * dh)          # QK^T + PV over all S keys
     attn += cfg.t2v_layers * H * (lv * s * dh + lv * lt * dh)  # scores over S keys, values over text only
     attn += cfg.enc_layers * H * (2 * lv * lv * dh)
-    return {"layer": 2.0 * layer, "gemm": 2.0 * (total - layer), "attention": 2.0 * attn}
+    inproj = (lv * cfg.v_feat_dim + lt * cfg.t_feat_dim) * d   # first projection layer (csrc/inproj.cu)
+    return {"layer": 2.0 * layer, "gemm": 2.0 * (total - layer - inproj), "attention": 2.0 * attn,
+            "inproj": 2.0 * inproj}

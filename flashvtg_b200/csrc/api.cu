@@ -54,7 +54,7 @@ struct Carver {
 
 struct Ws {
   // fusion
-  bf16 *vid_b, *txt_b, *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
+  bf16 *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
   float *Xf, *Yf, *pos_v, *pos_d, *tsum, *sal_scratch;
   // pyramid + heads
   bf16 *chain0, *chainA, *chainB, *H1, *H2, *hA, *hB, *mA, *mB;
@@ -66,12 +66,10 @@ struct Ws {
 static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws* w) {
   Carver k{base, 0};
   const size_t S = c.num_dummies + Lt;
-  const size_t Rv = static_cast<size_t>(Bc) * Lv, Rt = static_cast<size_t>(Bc) * Lt, Rs = Bc * S;
+  const size_t Rv = static_cast<size_t>(Bc) * Lv, Rs = Bc * S;
   const size_t Rmax = Rv > Rs ? Rv : Rs;
   PyrGeo g = make_geo(c, Lv, nullptr);
   Ws t;
-  t.vid_b = k.take<bf16>(Rv * c.v_dim_pad);
-  t.txt_b = k.take<bf16>(Rt * c.t_dim_pad);
   t.tmp256 = k.take<bf16>(Rmax * 256);
   t.Xf = k.take<float>(round_up_sz(Rs, 128) * 256);   // tile-blocked
   t.Xb = k.take<bf16>(Rs * 256);
@@ -225,18 +223,12 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
 }
 
 // LinearLayer x2 (model.py:99-110,782-789) for one modality.
-static int in_proj(cudaStream_t st, const FvtgInProj& P, const Ws& w, const float* src, bf16* stage,
-                   int rows, int dim, int dim_pad, GemmEpi final_epi) {
-  FVTG_TRY(launch_ln_cast(st, src, P.ln0.g, P.ln0.b, stage, rows, dim, dim_pad));
-  {  // tmp256 = bf16(LN1(relu(x W0^T + b0)))
-    GemmArgs g = gemm_args(rows, 256, 256, dim_pad);
-    g.epi.mode = EPI_ROW;
-    g.epi.bias = P.fc0.b;
-    g.epi.act = ACT_RELU;
-    g.epi.gamma = P.ln1.g; g.epi.beta = P.ln1.b;
-    g.epi.out_bf16 = w.tmp256;
-    FVTG_TRY(launch_gemm(st, stage, nullptr, rows, dim_pad, dim_pad, P.fc0.w, g));
-  }
+static int in_proj(cudaStream_t st, const FvtgInProj& P, const Ws& w, const float* src, int rows,
+                   int dim, int dim_pad, GemmEpi final_epi) {
+  // layer 0 with its LayerNorm over the raw dim folded in, + ReLU + LayerNorm(256) of layer 1:
+  // tmp256 = bf16(LN1(relu(LN0(x) W0^T + b0))), one pass over the fp32 features (inproj.cu)
+  FVTG_TRY(launch_inproj(st, src, rows, dim, dim_pad, P.fc0.w, P.fc0_wsum, P.fc0.b, P.ln1.g, P.ln1.b,
+                         w.tmp256));
   {
     GemmArgs g = gemm_args(rows, 256, 256, 256);
     g.epi = final_epi;
@@ -263,7 +255,7 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
     e.rowmap = RM_TXT; e.rm_a = Lt; e.rm_b = S; e.rm_c = nd;
     e.f32_blocked = 1;
     e.out_f32 = w.Xf; e.out_bf16 = w.Xb; e.out_bf16_pos = w.XPb; e.out_x1 = w.Kc;
-    FVTG_TRY(in_proj(st, W.txt, w, txt, w.txt_b, B * Lt, c.t_dim, c.t_dim_pad, e));
+    FVTG_TRY(in_proj(st, W.txt, w, txt, B * Lt, c.t_dim, c.t_dim_pad, e));
   }
   {  // video
     GemmEpi e;
@@ -271,7 +263,7 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
     e.f32_blocked = 1;
     e.out_f32 = w.Yf; e.out_bf16 = w.Yb; e.out_bf16_pos = w.YPb; e.pos = w.pos_v;
     e.pos_cmp_L = pos_cmp_L;
-    FVTG_TRY(in_proj(st, W.vid, w, vid, w.vid_b, B * Lv, c.v_dim, c.v_dim_pad, e));
+    FVTG_TRY(in_proj(st, W.vid, w, vid, B * Lv, c.v_dim, c.v_dim_pad, e));
   }
   for (int i = 0; i < c.dummy_layers; ++i) {
     // the last dummy layer writes bf16(dummy + dummy_pos) straight into the key rows of Kc

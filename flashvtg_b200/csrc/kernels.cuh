@@ -6,10 +6,10 @@
 namespace fvtg {
 
 // ---- prep.cu : HBM-bound staging ------------------------------------------------------------
-// LayerNorm over the raw feature dim (model.py:784-785) fused with the fp32 -> bf16 cast:
-// in fp32 [rows][dim] -> out bf16 [rows][dim_pad] (columns >= dim zero).
-int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const float* beta,
-                   bf16* out, int rows, int dim, int dim_pad);
+// inproj.cu: LayerNorm(raw dim) folded into the first projection GEMM, fp32 features read once:
+// out bf16 [rows][256] = bf16(LN_256(relu(LN_dim(x) . W^T + b))); wg = bf16(W * diag(gamma)) [256][dim_pad].
+int launch_inproj(cudaStream_t st, const float* x, int rows, int dim, int dim_pad, const void* wg,
+                  const float* wsum, const float* cfold, const float* g1, const float* b1, bf16* out);
 // Sine position table (position_encoding.py:61-72) for every video row of the chunk:
 // pos fp32 [B*Lv][256] in the tile-blocked layout; rows >= vlen[b] are zero.
 // compact: all videos of the chunk share vlen[0] -> pos is the [64][Lv][4] table (see prep.cu)

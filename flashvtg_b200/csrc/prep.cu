@@ -1,141 +1,9 @@
-// HBM-bound staging kernels: coalesced vector loads, warp-shuffle reductions, one pass over the
-// big fp32 inputs (the only place the 0.75-0.9 MB/video of features is read).
+// HBM-bound staging kernels: coalesced vector loads / stores (position tables, dummy-token rows,
+// pyramid level 0, layout conversion).  The big fp32 inputs are read by inproj.cu.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace fvtg {
-
-// LayerNorm over the raw feature dim + cast to bf16 (model.py:784-785 fused with operand staging).
-// TPR threads cooperate on one row and keep it in REGISTERS (one HBM read, no shared-memory
-// staging): every thread issues all of its <= 8 vector loads before the first reduction, so a
-// 256-thread CTA has 16-32 KB in flight - this kernel is the only reader of the 0.75 MB/video of
-// raw fp32 features and has to run at HBM speed.  Two-pass mean / variance like torch.
-template <int VEC, int TPR, int MAXV>
-__global__ void __launch_bounds__(256)
-ln_cast_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
-               const float* __restrict__ beta, bf16* __restrict__ out, int rows, int dim,
-               int dim_pad) {
-  constexpr int RPB = 256 / TPR;  // rows per block
-  __shared__ float s_red[2][8];
-  const int tid = threadIdx.x;
-  const int sub = tid / TPR, tl = tid % TPR;
-  const int row = blockIdx.x * RPB + sub;
-  const bool live = row < rows;
-  const int nvec = dim / VEC;  // dim % VEC == 0 is guaranteed by the launcher
-  float x[MAXV][VEC];
-  const float* src = in + static_cast<size_t>(live ? row : 0) * dim;
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = tl + i * TPR;
-    if (live && v < nvec) {
-      if (VEC == 4) {
-        const float4 t4 = __ldcs(reinterpret_cast<const float4*>(src) + v);
-        x[i][0] = t4.x; x[i][1 % VEC] = t4.y; x[i][2 % VEC] = t4.z; x[i][3 % VEC] = t4.w;
-      } else if (VEC == 2) {
-        const float2 t2 = __ldcs(reinterpret_cast<const float2*>(src) + v);
-        x[i][0] = t2.x; x[i][1 % VEC] = t2.y;
-      } else {
-        x[i][0] = __ldcs(src + v);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) x[i][e] = 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) sum += x[i][e];
-  }
-  // reduction over the TPR threads of the row (TPR is a multiple of 32)
-  auto row_sum = [&](float v, int slot) -> float {
-    v = warp_sum(v);
-    if (TPR == 32) return v;
-    const int w = tid >> 5, wpr = TPR / 32;
-    if ((tid & 31) == 0) s_red[slot][w] = v;
-    __syncthreads();
-    float tot = 0.f;
-#pragma unroll
-    for (int i = 0; i < wpr; ++i) tot += s_red[slot][(w / wpr) * wpr + i];
-    return tot;
-  };
-  const float mean = row_sum(sum, 0) / static_cast<float>(dim);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = tl + i * TPR;
-    if (v < nvec) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const float d = x[i][e] - mean;
-        sq += d * d;
-      }
-    }
-  }
-  const float rstd = rsqrtf(row_sum(sq, 1) / static_cast<float>(dim) + 1e-5f);
-  if (!live) return;
-  bf16* dst = out + static_cast<size_t>(row) * dim_pad;
-  const int nvec_pad = dim_pad / VEC;
-#pragma unroll
-  for (int i = 0; i < MAXV + 1; ++i) {
-    const int v = tl + i * TPR;
-    if (v >= nvec_pad) break;
-    float y[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) y[e] = 0.f;
-    if (i < MAXV && v < nvec) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e)
-        y[e] = (x[i < MAXV ? i : 0][e] - mean) * rstd * __ldg(gamma + v * VEC + e) + __ldg(beta + v * VEC + e);
-    }
-    if (VEC == 4) {
-      uint2 u;
-      u.x = pack_bf16(y[0], y[1 % VEC]);
-      u.y = pack_bf16(y[2 % VEC], y[3 % VEC]);
-      *reinterpret_cast<uint2*>(dst + v * 4) = u;
-    } else if (VEC == 2) {
-      *reinterpret_cast<uint32_t*>(dst + v * 2) = pack_bf16(y[0], y[1 % VEC]);
-    } else {
-      dst[v] = __float2bfloat16(y[0]);
-    }
-  }
-}
-
-template <int VEC>
-static int launch_ln_cast_v(cudaStream_t st, const float* in, const float* gamma, const float* beta,
-                            bf16* out, int rows, int dim, int dim_pad) {
-  const int nvec_pad = dim_pad / VEC;
-  // smallest TPR whose 8 vectors per thread cover the padded row; rows wider than 256 x 8 vectors
-  // (Charades-VGG: 4098 floats) take the 18-vector variant
-  int tpr = 32;
-  while (tpr < 256 && tpr * 8 < nvec_pad) tpr *= 2;
-  const bool wide = tpr * 8 < nvec_pad;
-  if (wide && tpr * 18 < nvec_pad) return fail(FVTG_EINVAL, "ln_cast: feature dim %d too large", dim);
-  const int rpb = 256 / tpr;
-  const int grid = (rows + rpb - 1) / rpb;
-  ProfScope prof(st, PC_LNCAST);
-  if (wide) {
-    ln_cast_kernel<VEC, 256, 18><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad);
-  } else {
-    switch (tpr) {
-      case 32: ln_cast_kernel<VEC, 32, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
-      case 64: ln_cast_kernel<VEC, 64, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
-      case 128: ln_cast_kernel<VEC, 128, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
-      default: ln_cast_kernel<VEC, 256, 8><<<grid, 256, 0, st>>>(in, gamma, beta, out, rows, dim, dim_pad); break;
-    }
-  }
-  FVTG_LAUNCH_CHECK("ln_cast_kernel");
-  return FVTG_OK;
-}
-
-int launch_ln_cast(cudaStream_t st, const float* in, const float* gamma, const float* beta,
-                   bf16* out, int rows, int dim, int dim_pad) {
-  if (rows <= 0) return FVTG_OK;
-  const uintptr_t ai = reinterpret_cast<uintptr_t>(in);
-  if (dim % 4 == 0 && dim_pad % 4 == 0 && (ai & 15) == 0)
-    return launch_ln_cast_v<4>(st, in, gamma, beta, out, rows, dim, dim_pad);
-  if (dim % 2 == 0 && dim_pad % 2 == 0 && (ai & 7) == 0)
-    return launch_ln_cast_v<2>(st, in, gamma, beta, out, rows, dim, dim_pad);
-  return launch_ln_cast_v<1>(st, in, gamma, beta, out, rows, dim, dim_pad);
-}
 
 // pos[b*Lv + i][c]: e = (i+1) / (len + 1e-6) * 2pi ; even c: sin(e / w_c), odd c: cos(e / w_c),
 // w_c = 10000^(2*floor(c/2)/256).

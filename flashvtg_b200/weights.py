@@ -155,7 +155,14 @@ class PackedWeights:
         for name, dst, dim, row in (("input_vid_proj", w.vid, cfg.v_feat_dim, 1),
                                     ("input_txt_proj", w.txt, cfg.t_feat_dim, 0)):
             ln(dst.ln0, f"{name}.0.LayerNorm")
-            lin(dst.fc0, sd[f"{name}.0.net.1.weight"], sd[f"{name}.0.net.1.bias"], pad64(dim))
+            # LayerNorm(raw dim) folded into the first projection (csrc/inproj.cu):
+            #   LN(x) W^T + b = rstd * ((x - m0) Wg^T - mean(x - m0) * rowsum(Wg)) + (W beta + b)
+            w0 = sd[f"{name}.0.net.1.weight"].float()
+            g0 = sd[f"{name}.0.LayerNorm.weight"].float()
+            b0 = sd[f"{name}.0.LayerNorm.bias"].float()
+            wg = w0 * g0[None, :]
+            lin(dst.fc0, wg, w0 @ b0 + sd[f"{name}.0.net.1.bias"].float(), pad64(dim))
+            dst.fc0_wsum = f32(wg.to(torch.bfloat16).float().sum(1))
             ln(dst.ln1, f"{name}.1.LayerNorm")
             # token_type_embeddings row folded into the bias (model.py:151-152)
             lin(dst.fc1, sd[f"{name}.1.net.1.weight"], sd[f"{name}.1.net.1.bias"].float() + te[row])

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FVTG_ABI_VERSION 1
+#define FVTG_ABI_VERSION 2
 
 #define FVTG_OK 0
 #define FVTG_EINVAL (-1)   /* bad shape / config / null pointer */
@@ -85,10 +85,12 @@ typedef struct FvtgLinear {
 } FvtgLinear;
 
 typedef struct FvtgInProj {  /* LinearLayer x2, model.py:767-789 */
-  FvtgLN ln0;       /* over the raw feature dim */
-  FvtgLinear fc0;   /* [256][dim_pad] */
+  FvtgLN ln0;       /* over the raw feature dim (kept for reference; folded into fc0, see below) */
+  FvtgLinear fc0;   /* LayerNorm-folded first layer: w = bf16(W * diag(gamma_ln0)) [256][dim_pad],
+                       b = W . beta_ln0 + bias (fp32 [256]) */
   FvtgLN ln1;       /* over 256 */
   FvtgLinear fc1;   /* [256][256]; bias has token_type_embeddings row folded in */
+  const float* fc0_wsum;  /* fp32 [256]: row sums of fc0.w as stored (bf16 values), for the mean correction */
 } FvtgInProj;
 
 typedef struct FvtgEncLayer {  /* transformer.py:387-421 / :311-369 */
@@ -261,7 +263,7 @@ int32_t fvtg_abi_version(void);
 
 /* Bench hook.  fvtg_prof_enable(1): every kernel launched by this thread's later fvtg_* calls is
  * bracketed by a CUDA event pair on its stream.  fvtg_prof_collect waits for them and returns, per
- * kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm+cast staging, 3 decode/NMS, 4 other,
+ * kernel class (0 tcgen05 GEMM, 1 attention, 2 fused first input projection, 3 decode/NMS, 4 other,
  * 5 fused tcgen05 transformer-layer kernel),
  * the summed device time in ms and the launch count since the last collect. */
 #define FVTG_PROF_CLASSES 6

@@ -38,8 +38,20 @@ def _prelu(x, a):
 
 
 def input_proj(x, sd, name, te_row):
-    a = q(_ln(x, sd, f"{name}.0.LayerNorm"))
-    t = q(_ln(torch.relu(_lin(a, sd, f"{name}.0.net.1")), sd, f"{name}.1.LayerNorm"))
+    """csrc/inproj.cu: LayerNorm over the raw dim folded into the first projection.  The kernel rounds the
+    SHIFTED raw values (x - m0, m0 = mean of the row's first 64 values) and W * gamma to bf16, accumulates in
+    fp32 and applies mean / rstd of the shifted row in the epilogue."""
+    w0, b0 = sd[f"{name}.0.net.1.weight"], sd[f"{name}.0.net.1.bias"]
+    g0, be0 = sd[f"{name}.0.LayerNorm.weight"], sd[f"{name}.0.LayerNorm.bias"]
+    dim = x.shape[-1]
+    m0 = x[:, : min(64, dim)].mean(-1, keepdim=True)
+    xs = x - m0
+    wg = q(w0 * g0[None, :])
+    ms = xs.mean(-1, keepdim=True)
+    var = ((xs * xs).mean(-1, keepdim=True) - ms * ms).clamp_min(0)
+    rstd = torch.rsqrt(var + 1e-5)
+    y = rstd * (q(xs) @ wg.t() - ms * wg.sum(1)[None, :]) + (w0 @ be0 + b0)[None, :]
+    t = q(_ln(torch.relu(y), sd, f"{name}.1.LayerNorm"))
     return _lin(t, sd, f"{name}.1.net.1", te_row)
 
 

@@ -39,7 +39,7 @@ def test_ctypes_structs_match_the_c_header():
     from flashvtg_b200 import _lib
     structs = {"FvtgCfg": ["abi_version", "max_num_moment", "clip_len"],
                "FvtgLN": ["g", "b"], "FvtgLinear": ["w", "b"],
-               "FvtgInProj": ["ln0", "fc0", "ln1", "fc1"],
+               "FvtgInProj": ["ln0", "fc0", "ln1", "fc1", "fc0_wsum"],
                "FvtgEncLayer": ["in_proj", "out_proj", "norm1", "ff1", "ff2", "norm2", "prelu"],
                "FvtgPyrConv": ["conv", "ln"],
                "FvtgScoreHead": ["conv", "mlp", "last_w", "last_b"],
@@ -159,6 +159,11 @@ def test_packed_layouts_fold_taps_and_token_type():
     assert torch.allclose(b, sd["input_vid_proj.1.net.1.bias"] + sd["token_type_embeddings.weight"][1])
     fc0 = by_ptr[W.struct.vid.fc0.w]
     assert fc0.shape == (256, 832) and float(fc0[:, 770:].abs().sum()) == 0.0
+    # LayerNorm over the raw dim is folded into the first projection (csrc/inproj.cu)
+    w0, g0, b0 = (sd[f"input_vid_proj.0.{n}"] for n in ("net.1.weight", "LayerNorm.weight", "LayerNorm.bias"))
+    assert torch.equal(fc0[:, :770].float(), (w0 * g0[None, :]).to(torch.bfloat16).float())
+    assert torch.allclose(by_ptr[W.struct.vid.fc0.b], w0 @ b0 + sd["input_vid_proj.0.net.1.bias"], atol=1e-6)
+    assert torch.allclose(by_ptr[W.struct.vid.fc0_wsum], fc0.float().sum(1), atol=1e-5)
     c2 = by_ptr[W.struct.coord2.w]
     assert c2.shape == (16, 768) and float(c2[2:].abs().sum()) == 0.0
 
