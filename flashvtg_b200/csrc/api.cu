@@ -305,6 +305,18 @@ static int score_head(cudaStream_t st, const FvtgCfg& c, const FvtgScoreHead& H,
     FVTG_TRY(launch_gemm(st, cur, nullptr, rows, 256, 256, H.conv[ci].w, g));
     cur = bufs[ci & 1];
   }
+  {  // the whole MLP behind the convs in one kernel (mlp.cu); FVTG_MLP_FUSED=0 keeps the per-layer GEMMs
+    static const bool fused = [] { const char* e = getenv("FVTG_MLP_FUSED"); return !e || atoi(e) != 0; }();
+    if (fused && c.num_mlp_layers - 1 <= 7) {
+      MlpHostArgs h;
+      memset(&h, 0, sizeof(h));
+      h.M = rows; h.nl = c.num_mlp_layers - 1; h.h2 = rowmap == RM_H2 ? 1 : 0;
+      h.last_b = H.last_b; h.last_w = H.last_w; h.out = out_logit; h.geo = geo;
+      const void* wp[7];
+      for (int m = 0; m < h.nl; ++m) { h.bias[m] = H.mlp[m].b; wp[m] = H.mlp[m].w; }
+      return launch_mlp_chain(st, cur, wp, h);
+    }
+  }
   bf16* mb[2] = {w.mA, w.mB};
   int kin = 256;
   for (int m = 0; m < c.num_mlp_layers - 1; ++m) {

@@ -50,6 +50,18 @@ int launch_layer_pair(cudaStream_t st, const bf16* att, const bf16* wo, const bf
 // fp32 tile-blocked rows -> row-major fp32: dst[(b * rows_out + j)][256] = src row (b * rows_in + j), j < rows_out
 int launch_unblock(cudaStream_t st, const float* src_blk, float* dst, int B, int rows_in, int rows_out);
 
+// ---- mlp.cu : score-head MLP chain (Linear 256->128, ReLU, [Linear 128->128, ReLU]*, Linear 128->1) fused,
+// activations in TMEM; a = head conv output bf16 [M][256], w[m] bf16 [128][256 | 128], logits -> out[b][n]
+struct MlpHostArgs {
+  int M, nl, h2;          // rows of the head row space, hidden layers, 0 = H1 (class) / 1 = H2 (conf)
+  float last_b;
+  const float* bias[7];
+  const float* last_w;
+  float* out;
+  PyrGeo geo;
+};
+int launch_mlp_chain(cudaStream_t st, const bf16* a, const void* const* w, const MlpHostArgs& h);
+
 // ---- attn.cu : per-(video, head) attention on legacy warp MMA ----------------------------------
 struct AttnArgs {
   const bf16* q; int ldq;   // query rows  [b*Lq + i][ldq], head h at columns h*32
