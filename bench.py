@@ -37,7 +37,7 @@ B_PER_GPU, LV, LT = 1024, 75, 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class, from the committed
 # `ncu --set full` capture of this command (profiles/); None until a capture exists.
 # layer: profiles/r01g_summary.md (T2V-layer launches: 119.4 MB read + 65.0 / 69.6 MB written)
-NCU_TRAFFIC = {"layer": 1.866e8, "gemm": None, "attention": None}
+NCU_TRAFFIC = {"layer": 1.838e8, "gemm": None, "attention": None}
 
 
 def workload_config(n_gpus):

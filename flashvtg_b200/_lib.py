@@ -135,6 +135,8 @@ SIGNATURES = {
     "fvtg_prof_enable": (None, [i32]),
     "fvtg_prof_collect": (i32, [vp, vp, i32]),
     "fvtg_dbg_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "fvtg_dbg_stream_probe": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "fvtg_dbg_inproj": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

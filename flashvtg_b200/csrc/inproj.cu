@@ -21,6 +21,13 @@
 // loads (row pitches of the TEF-appended features are only 8-byte aligned, so TMA cannot fetch
 // them), keeps the next k-block's loads in flight while it converts the current one, and writes
 // bf16 pairs straight into the SWIZZLE_128B A tile.
+//
+// What bounds it (tools/probe_stream.py, tools/trace_inproj.py, profiles/r01i_inproj_notes.md): the
+// k-block shape - 128 rows x 256 B per step, every row another DRAM page - streams at 3.8 TB/s on a
+// B200 even with nothing but cp.async copies (512 B per row: 4.7, 1 KB: 5.2, 2 KB: 5.4 TB/s); the
+// text projection runs at 3.0 TB/s of that, the short-K video projection is bound by the two-pass
+// epilogue of its 4 epilogue warps.  A cp.async-staged variant (3 x 32 KB fp32 slots) and equal
+// row ranges per SM were built and measured: no faster, because the limit is the access shape.
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -103,7 +110,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ I
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < g.kbs; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_sleep(&empty[s], ph ^ 1, 64);
           mbar_expect_tx(&full[s], IP_B_BYTES);
           tma_load_2d(smem + s * IP_STAGE_BYTES + IP_A_BYTES, &tmB, kb * 64, 0, &full[s]);
           if (++s == IP_STAGES) { s = 0; ph ^= 1; }
@@ -123,6 +130,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ I
         const uint32_t tacc = tmem_base + acc * 256;
         for (int kb = 0; kb < g.kbs; ++kb) {
           mbar_wait(&full[s], ph);
+          fence_proxy_async_smem();   // the converters' generic-proxy stores -> tensor-core reads
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * IP_STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + IP_A_BYTES);
@@ -188,7 +196,8 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ I
           *reinterpret_cast<uint32_t*>(sa + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) =
               pack_bf16(a, b);
         }
-        fence_proxy_async_smem();
+        // no proxy fence here (it is a MEMBAR.ALL.CTA that would wait for the loads in flight): the
+        // arrive releases the stores to the MMA thread, which fences generic -> async proxy itself
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
         if (++s == IP_STAGES) { s = 0; ph ^= 1; }
@@ -221,8 +230,8 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ I
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
       const int row = tile * 128 + r;
-      mbar_wait(&tfull[acc], accph);
-      mbar_wait(&sfull[acc], accph);
+      mbar_wait_sleep(&tfull[acc], accph, 256);   // long by design: do not poll the issue slots away
+      mbar_wait_sleep(&sfull[acc], accph, 64);
       tc_fence_after();
       const uint32_t tacc = tmem_base + acc * 256 + (static_cast<uint32_t>(wq * 32) << 16);
       const float2 st = s_stat[acc * 128 + r];
@@ -306,3 +315,11 @@ int launch_inproj(cudaStream_t st, const float* x, int rows, int dim, int dim_pa
 }
 
 }  // namespace fvtg
+
+// debug / tuning entry: the fused first projection alone (tools/trace_inproj.py)
+extern "C" int32_t fvtg_dbg_inproj(const float* x, int32_t rows, int32_t dim, int32_t dim_pad, const void* wg,
+                                   const float* wsum, const float* cfold, const float* g1, const float* b1,
+                                   void* out, void* stream) {
+  return fvtg::launch_inproj(static_cast<cudaStream_t>(stream), x, rows, dim, dim_pad, wg, wsum, cfold, g1, b1,
+                             static_cast<fvtg::bf16*>(out));
+}

@@ -244,6 +244,72 @@ mma_rate_probe2_kernel(int N, int iters, int ts, long long* out_cycles) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fvtg_dbg_stream_probe: how fast can 148 CTAs stream an fp32 [rows][dim] matrix with the access
+// shape of the first-projection kernel?  16 warps per CTA, warp w owns rows 8w..8w+7 of each
+// 128-row tile and copies 2 KB chunks (8 cp.async of 8 B per lane) into private shared-memory
+// slots, `slots` deep.  seg = 256-byte segments taken from ONE row per chunk: seg 1 is the k-block
+// shape (8 rows x 256 B, every row a different DRAM page), seg 8 is 1 row x 2 KB contiguous.
+__global__ void __launch_bounds__(512, 1)
+stream_probe_kernel(const float* x, int rows, int dim, int seg, int slots, int cta_rows, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_begin = blockIdx.x * cta_rows;
+  const int cta_end = min(cta_begin + cta_rows, rows);
+  const int n_tiles = cta_end > cta_begin ? (cta_end - cta_begin) / 128 : 0;
+  const int kbs = dim / 64;
+  const int rows_per_chunk = 8 / seg;
+  const int chunks_per_tile = kbs;   // 8 rows x kbs x 256 B per warp, 2 KB per chunk
+  const uint32_t my = smem_u32(smem) + warp * 2048 + lane * 8;
+  const size_t pitch = static_cast<size_t>(dim) * 4;
+  const int total = n_tiles * chunks_per_tile;
+  int pf = 0, pf_slot = 0;
+  auto issue = [&]() {
+    if (pf < total) {
+      const int tile = pf / chunks_per_tile, c = pf - tile * chunks_per_tile;
+      // chunk c: super-block sb of `seg` k-blocks, row group rg inside it
+      const int groups = 8 / rows_per_chunk;            // == seg
+      const int sb = c / groups, rg = c - sb * groups;
+      const char* base = reinterpret_cast<const char*>(x) +
+                         static_cast<size_t>(cta_begin + tile * 128 + warp * 8 + rg * rows_per_chunk) * pitch +
+                         static_cast<size_t>(sb) * seg * 256 + lane * 8;
+      const uint32_t dst = my + pf_slot * 32768;
+      int i = 0;
+      for (int r = 0; r < rows_per_chunk; ++r)
+        for (int sgm = 0; sgm < seg; ++sgm, ++i)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 256),
+                       "l"(base + r * pitch + sgm * 256) : "memory");
+      ++pf;
+      if (++pf_slot == slots) pf_slot = 0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int i = 0; i < slots; ++i) issue();
+  float acc = 0.f;
+  int slot = 0;
+  for (int q = 0; q < total; ++q) {
+    switch (slots) {
+      case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+      case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+      case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      case 5: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+      default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    }
+    const uint32_t src = my + slot * 32768;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a, b;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(src + j * 256));
+      acc += a + b;
+    }
+    issue();
+    if (++slot == slots) slot = 0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (acc == 123.456f) out[0] = acc;
+}
+
 }  // namespace fvtg
 
 extern "C" int32_t fvtg_dbg_tma_probe(const void* w_bf16 /* [rows][256] */, int32_t rows, int32_t stages,
@@ -335,5 +401,21 @@ extern "C" int32_t fvtg_dbg_mma_probe2(int32_t N, int32_t iters, int32_t cg, int
   if (cg == 2) FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, mma_rate_probe2_kernel<2>, N, iters, ts, oc));
   else FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, mma_rate_probe2_kernel<1>, N, iters, ts, oc));
   count_launch();
+  return FVTG_OK;
+}
+
+extern "C" int32_t fvtg_dbg_stream_probe(const float* x, int32_t rows, int32_t dim, int32_t seg, int32_t slots,
+                                         float* out, void* stream) {
+  using namespace fvtg;
+  if ((seg != 1 && seg != 2 && seg != 4 && seg != 8) || slots < 2 || slots > 6 || dim % (64 * seg) || rows % 128)
+    return fail(FVTG_EINVAL, "stream probe: bad arguments");
+  const int smem = slots * 32768;
+  FVTG_CUDA_OK(cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int tiles = rows / 128;
+  const int ctas = tiles < sm_count() ? tiles : sm_count();
+  const int cta_rows = (tiles + ctas - 1) / ctas * 128;
+  const int grid = (rows + cta_rows - 1) / cta_rows;
+  stream_probe_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(x, rows, dim, seg, slots, cta_rows, out);
+  FVTG_LAUNCH_CHECK("stream_probe_kernel");
   return FVTG_OK;
 }

@@ -280,6 +280,14 @@ void fvtg_dbg_set_trace(void* device_buf);
 int32_t fvtg_dbg_gemm(const void* a, const void* w, const float* bias, float* out, int32_t M,
                       int32_t N, int32_t K, int32_t act, void* stream);
 
+/* Test / tuning hook: the fused first input projection alone (FvtgInProj.fc0 semantics):
+ * out bf16 [rows][256] = LN_256(ReLU(LN_dim(x) . W^T + b)) with x fp32 [rows][dim] (dim even),
+ * wg bf16 [256][dim_pad] = W . diag(gamma) zero padded to dim_pad (multiple of 64), wsum = row sums
+ * of wg, cfold = W . beta + b, (g1, b1) the LayerNorm(256) of the next layer. */
+int32_t fvtg_dbg_inproj(const float* x, int32_t rows, int32_t dim, int32_t dim_pad, const void* wg,
+                        const float* wsum, const float* cfold, const float* g1, const float* b1,
+                        void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
