@@ -112,6 +112,12 @@ class FvtgRawBatch(C.Structure):
                 ("vid", vp * RAW_MAX_GROUPS), ("txt", vp), ("vid_len", vp), ("txt_len", vp)]
 
 
+class FvtgEvalBatch(C.Structure):
+    _fields_ = [("n_queries", i32), ("max_pred", i32), ("max_gt", i32), ("max_sal", i32), ("max_clips", i32),
+                ("_pad", i32), ("pred_win", vp), ("pred_cnt", vp), ("gt_win", vp), ("gt_cnt", vp),
+                ("pred_sal", vp), ("pred_sal_len", vp), ("gt_sal", vp), ("gt_clips", vp)]
+
+
 # name -> (restype, argtypes); also the list the ABI test checks against the header.
 SIGNATURES = {
     "fvtg_workspace_bytes": (C.c_size_t, [C.POINTER(FvtgCfg), i32, i32, i32]),
@@ -128,6 +134,7 @@ SIGNATURES = {
                            C.POINTER(FvtgDecodeParams), C.POINTER(FvtgFusionOut),
                            C.POINTER(FvtgHeadsOut), C.POINTER(FvtgDecodeOut), vp, C.c_size_t, vp]),
     "fvtg_prepare_inputs": (i32, [C.POINTER(FvtgRawBatch), vp, vp, vp, vp, vp]),
+    "fvtg_eval_submission": (i32, [C.POINTER(FvtgEvalBatch), i32, vp, vp, vp, vp, vp, vp]),
     "fvtg_last_launch_count": (C.c_int64, []),
     "fvtg_last_error": (C.c_char_p, []),
     "fvtg_abi_version": (i32, []),

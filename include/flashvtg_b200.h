@@ -256,6 +256,37 @@ typedef struct FvtgRawBatch {
 int32_t fvtg_prepare_inputs(const FvtgRawBatch* raw, float* src_vid, float* src_vid_mask,
                             float* src_txt, float* src_txt_mask, void* stream);
 
+/* ---- QVHighlights evaluation on the device (what standalone_eval does per query on the host) ----
+ * Replaces the per-query loops of standalone_eval/eval.py: compute_mr_ap (:24-69, detection AP of
+ * utils.py:83-159 at IoU 0.5..0.95), compute_mr_r1 (:72-102), the length ranges of
+ * eval_moment_retrieval (:109-170: 0 short (0,10], 1 middle (10,30], 2 long (30,150], 3 full),
+ * compute_hl_hit1 / compute_hl_ap (:173-236, get_ap of utils.py:162-209 for minimum scores 2,3,4 and the
+ * 3 annotators).  All arithmetic in fp64, in numpy's operation order (pairwise sums included), so the
+ * per-query results are bit-identical; the means over queries and the 2-decimal formatting stay on the
+ * host (flashvtg_b200/evaluation.py).  One row per query; every pointer is device memory. */
+typedef struct FvtgEvalBatch {
+  int32_t n_queries;
+  int32_t max_pred;              /* row stride of pred_win (windows per query) */
+  int32_t max_gt;                /* row stride of gt_win, <= 32 */
+  int32_t max_sal;               /* row stride of pred_sal */
+  int32_t max_clips;             /* row stride of gt_sal */
+  int32_t _pad;
+  const double* pred_win;        /* [Q][max_pred][3] (start, end, score) in submission order */
+  const int32_t* pred_cnt;       /* [Q] */
+  const double* gt_win;          /* [Q][max_gt][2] relevant_windows */
+  const int32_t* gt_cnt;         /* [Q] */
+  const double* pred_sal;        /* [Q][max_sal] pred_saliency_scores (null: no highlight metrics) */
+  const int32_t* pred_sal_len;   /* [Q] */
+  const uint8_t* gt_sal;         /* [Q][max_clips][3] annotator scores 0..4 of every clip (mk_gt_scores) */
+  const int32_t* gt_clips;       /* [Q] int(duration / clip_length) */
+} FvtgEvalBatch;
+/* mr_ap fp64 [4][Q][10], mr_iou fp64 [4][Q] (top-1 IoU with the best GT window), mr_valid u8 [4][Q]
+ * (query has a GT window in the range); hl_ap fp64 [3][Q][3] (min score, query, annotator), hl_hit u8
+ * [3][Q].  Pass mr_ap == null or hl_ap == null to skip a family.  max_pred_windows: the reference's 10. */
+int32_t fvtg_eval_submission(const FvtgEvalBatch* batch, int32_t max_pred_windows, double* mr_ap,
+                             double* mr_iou, uint8_t* mr_valid, double* hl_ap, uint8_t* hl_hit,
+                             void* stream);
+
 /* Number of kernel launches the last fvtg_* compute call on this thread issued. */
 int64_t fvtg_last_launch_count(void);
 const char* fvtg_last_error(void);

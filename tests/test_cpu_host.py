@@ -48,6 +48,8 @@ def test_ctypes_structs_match_the_c_header():
                "FvtgBatch": ["B", "Lv", "Lt", "uniform_vid_len", "vid", "txt", "vid_len", "txt_len"],
                "FvtgRawBatch": ["B", "Lv", "Lt", "n_groups", "group_dim", "t_dim", "dtype", "normalize_v",
                                 "normalize_t", "use_tef", "vid", "txt", "vid_len", "txt_len"],
+               "FvtgEvalBatch": ["n_queries", "max_pred", "max_gt", "max_sal", "max_clips", "pred_win", "pred_cnt",
+                                 "gt_win", "gt_cnt", "pred_sal", "pred_sal_len", "gt_sal", "gt_clips"],
                "FvtgFusionOut": ["video_emb", "saliency", "t2v", "dummy_tokens"],
                "FvtgHeadsOut": ["n_max", "cls_logit", "conf_logit", "coord"],
                "FvtgDecodeParams": ["nms_thd", "x", "clip_len", "inv_clip_len", "min_ts", "max_ts",
