@@ -36,7 +36,7 @@ PRESET = "qvh_iv2"
 B_PER_GPU, LV, LT = 1024, 75, 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class, from the committed
 # `ncu --set full` capture of this command (profiles/); None until a capture exists.
-# layer: profiles/r01g_summary.md (T2V-layer launches: 119.4 MB read + 65.0 / 69.6 MB written)
+# layer: profiles/r01h_summary.md (T2V-layer launches: 119.3 MB read + 64.7 / 64.1 MB written)
 NCU_TRAFFIC = {"layer": 1.838e8, "gemm": None, "attention": None}
 
 
@@ -338,7 +338,7 @@ def run_ours(args):
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         fl = flops_by_kernel_class(cfg, LV, LT)
         names = {"layer": "layer_kernel (tcgen05/TMEM + TMA: out_proj + LN1 + FFN + LN2 fused)",
-                 "gemm": "gemm_kernel (persistent tcgen05/TMEM + TMA GEMM, fused epilogues)",
+                 "gemm": "gemm_kernel + mlp_chain_kernel (persistent tcgen05/TMEM + TMA GEMMs, fused epilogues; score-head MLP chained in TMEM)",
                  "attention": "attention_kernel (per video x 4-head group, mma.sync)",
                  "inproj": "inproj_kernel (LayerNorm-folded first projection, fp32 features read once, tcgen05)"}
         cls_ms = {n: ms_c[i] / ksteps for i, n in enumerate(_lib.PROF_CLASSES)}
