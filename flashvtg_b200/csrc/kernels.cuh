@@ -40,6 +40,8 @@ struct LayerArgs {
   long long* trace;  // debug: per-phase clock64 stamps of CTA 0 (fvtg_dbg_set_trace), null in production
   int stagger_ns;    // start-up delay step: cluster c sleeps (c % 8) * stagger_ns before its first tile
   int dbg;           // debug (env FVTG_LAYER_DBG): bit 0 skip residual loads, bit 1 skip pos loads, bit 2 skip global stores
+  int tile_rows;     // rows a tile advances by (<= 128, multiple of 8; set by launch_layer): the MMAs always run
+                     // M = 128, rows past tile_rows belong to the next tile and are computed but not stored
 };
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args);
