@@ -156,7 +156,12 @@ attention_kernel(const AttnArgs a, const int Lkpad) {
 // staged once with coalesced 16-byte cp.async (row pitch 272 B keeps ldmatrix conflict-free), the
 // whole score row lives in registers (no online softmax), the output tile goes back through
 // shared memory so that global stores are 16 bytes per lane.  ~65 KB of shared memory and <= 85
-// registers keep 3 CTAs (24 warps) per SM: the kernel is issue-bound on the softmax, not on MMA.
+// registers keep 3 CTAs (24 warps) per SM: the kernel is issue-bound on the softmax, not on MMA
+// (ncu: ~730 SASS instructions per 16-row unit before the masking was made branch-free, 40 of them HMMA).
+// A persistent variant with double-buffered K / V staging, Q fragments read straight from global memory
+// and 2 balanced units per warp was built and measured (commit "Attention: branch-free key/value
+// masking ..."): 0.70 ms/step against 0.56 for this kernel - its exposed L2 latency on the Q fragments
+// and the lower warp count per SM cost more than the hidden staging saves - so it was dropped.
 constexpr int AV_PITCH = 136;  // bf16 elements per staged row (4 heads x 32 + 8 pad)
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -336,235 +341,6 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
   AT_TRACE(4);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Streaming variant of the kernel above (default for QVHighlights-sized sequences): persistent CTAs
-// walk the (video, head group) items with the K / V slices of the NEXT item in flight (cp.async
-// into the other half of a double buffer) while the warps compute the current one, so the ~6 k
-// cycles of staging latency and the CTA launch / drain of the one-shot kernel disappear from the
-// SM's timeline.  To make double buffering affordable in shared memory only K / V are staged:
-//   * Q fragments (16 rows x 32 columns per unit) are read straight from global memory in the
-//     mma A-fragment layout (4-byte loads, 16 contiguous bytes per row quad) BEFORE the wait for the
-//     item's K / V, so their latency hides behind it;
-//   * the normalised output goes from the accumulator registers to global memory directly.
-// A CTA has W warps for HG heads x ceil(Lq / 16) m-tiles = units; with HG = 4, W = 10 (cross
-// attention, K = V shared) and HG = 2, W = 5 (self attention) a 75-clip video gives every warp
-// exactly two units - the one-shot kernel's 20 units on 8 warps cost three rounds.
-template <int NT, bool KV_SHARED, int HG, int W>
-__global__ void __launch_bounds__(W * 32, KV_SHARED ? 2 : 4)
-attn_stream_kernel(const AttnArgs a) {
-  constexpr int LkPad = NT * 8;
-  constexpr int PITCH = HG * 32 + 8;            // bf16 elements per staged row
-  constexpr int CHUNKS = HG * 4;                // 16-byte chunks per row
-  constexpr int BUF = LkPad * PITCH * (KV_SHARED ? 1 : 2);
-  extern __shared__ __align__(16) uint8_t as_smem[];
-  bf16* sbuf = reinterpret_cast<bf16*>(as_smem);   // [2][BUF]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  constexpr int GROUPS = 8 / HG;                // head groups per video
-  const int items = a.B * GROUPS;
-  const int m_tiles = (a.Lq + 15) >> 4;
-  const int units = HG * m_tiles;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  auto stage = [&](int item, int which) {
-    const int b = item / GROUPS, col0 = (item - b * GROUPS) * (HG * 32);
-    int klen = a.kbase + a.klen_src[b];
-    if (klen > a.Lk) klen = a.Lk;
-    bf16* sK = sbuf + which * BUF;
-    bf16* sV = sK + LkPad * PITCH;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    for (int idx = tid; idx < LkPad * CHUNKS; idx += W * 32) {
-      const int r = idx / CHUNKS, c = idx - r * CHUNKS;
-      const size_t grow = static_cast<size_t>(b) * a.Lk + r;
-      bf16* dk = sK + r * PITCH + c * 8;
-      if (r < klen) cp_async16(smem_u32(dk), a.k + grow * a.ldk + col0 + c * 8);
-      else *reinterpret_cast<uint4*>(dk) = zero4;
-      if (!KV_SHARED) {
-        bf16* dv = sV + r * PITCH + c * 8;
-        if (r < klen) cp_async16(smem_u32(dv), a.v + grow * a.ldv + col0 + c * 8);
-        else *reinterpret_cast<uint4*>(dv) = zero4;
-      }
-    }
-  };
-  auto load_q = [&](int b, int col0, int u, uint32_t (&aq)[2][4]) {
-    const int hl = u % HG, mt = u / HG;
-    const int r0 = min(mt * 16 + g, a.Lq - 1), r1 = min(mt * 16 + g + 8, a.Lq - 1);   // dead rows: any valid row
-    const bf16* q0 = a.q + (static_cast<size_t>(b) * a.Lq + r0) * a.ldq + col0 + hl * 32 + 2 * t;
-    const bf16* q1 = a.q + (static_cast<size_t>(b) * a.Lq + r1) * a.ldq + col0 + hl * 32 + 2 * t;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      aq[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q0 + ks * 16));
-      aq[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q1 + ks * 16));
-      aq[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8));
-      aq[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8));
-    }
-  };
-  const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
-  auto compute = [&](int b, int col0, int klen, const bf16* sK, const bf16* sV, int u, const uint32_t (&aq)[2][4]) {
-    const int hl = u % HG, mt = u / HG;
-    float s[NT][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      uint32_t kb[4];
-      ldmatrix_x4(kb, smem_u32(sK + (nt * 8 + (lane & 7)) * PITCH + hl * 32 + (lane >> 3) * 8));
-      mma16816(s[nt], aq[0], kb[0], kb[1]);
-      mma16816(s[nt], aq[1], kb[2], kb[3]);
-    }
-    // Key rows >= klen are zero in shared memory, so their scores are exactly 0: the stabilising
-    // offset may include them (softmax is shift invariant) and needs no masking; their probabilities
-    // are forced to 0 below with two compares per tile against this lane's column limit - branch-free,
-    // no per-tile control flow for the register allocator to patch up with moves.
-    float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), 0.f), mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), 0.f);
-#pragma unroll
-    for (int nt = 1; nt < NT; ++nt) {
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float off0 = mx0 * sc, off1 = mx1 * sc;
-    const int lim = klen - 2 * t;          // column c of tile nt is a valid key  <=>  nt * 8 + c < lim
-    const int vlim = a.v_first - 2 * t;    // ... carries a value              <=>  nt * 8 + c >= vlim
-    float l0 = 0.f, l1 = 0.f, ts0 = 0.f, ts1 = 0.f;
-    if (a.v_first > 0) {
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const bool k0 = nt * 8 < lim, k1 = nt * 8 + 1 < lim;
-        const bool v0 = nt * 8 >= vlim, v1 = nt * 8 + 1 >= vlim;
-        float p0 = ex2_approx(fmaf(s[nt][0], sc, -off0));
-        float p1 = ex2_approx(fmaf(s[nt][1], sc, -off0));
-        float p2 = ex2_approx(fmaf(s[nt][2], sc, -off1));
-        float p3 = ex2_approx(fmaf(s[nt][3], sc, -off1));
-        p0 = k0 ? p0 : 0.f; p1 = k1 ? p1 : 0.f; p2 = k0 ? p2 : 0.f; p3 = k1 ? p3 : 0.f;
-        l0 += p0 + p1;
-        l1 += p2 + p3;
-        s[nt][0] = v0 ? p0 : 0.f; s[nt][1] = v1 ? p1 : 0.f;     // dummies absorb mass, carry no value
-        s[nt][2] = v0 ? p2 : 0.f; s[nt][3] = v1 ? p3 : 0.f;
-        ts0 += s[nt][0] + s[nt][1];
-        ts1 += s[nt][2] + s[nt][3];
-      }
-    } else {
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const bool k0 = nt * 8 < lim, k1 = nt * 8 + 1 < lim;
-        const float p0 = ex2_approx(fmaf(s[nt][0], sc, -off0));
-        const float p1 = ex2_approx(fmaf(s[nt][1], sc, -off0));
-        const float p2 = ex2_approx(fmaf(s[nt][2], sc, -off1));
-        const float p3 = ex2_approx(fmaf(s[nt][3], sc, -off1));
-        s[nt][0] = k0 ? p0 : 0.f; s[nt][1] = k1 ? p1 : 0.f;
-        s[nt][2] = k0 ? p2 : 0.f; s[nt][3] = k1 ? p3 : 0.f;
-        l0 += s[nt][0] + s[nt][1];
-        l1 += s[nt][2] + s[nt][3];
-      }
-      ts0 = l0;
-      ts1 = l1;
-    }
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < NT / 2; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-      const int krow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      const uint32_t vb = smem_u32(sV + krow * PITCH + hl * 32 + (lane >> 4) * 8);
-      uint32_t v0[4], v1[4];
-      ldmatrix_x4_trans(v0, vb);
-      ldmatrix_x4_trans(v1, vb + 32);
-      mma16816(o[0], pa, v0[0], v0[1]);
-      mma16816(o[1], pa, v0[2], v0[3]);
-      mma16816(o[2], pa, v1[0], v1[1]);
-      mma16816(o[3], pa, v1[2], v1[3]);
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
-    const int r0 = mt * 16 + g, r1 = r0 + 8;
-    // lanes t and t^1 swap halves so that every lane stores 8 contiguous bytes (4 columns) per row
-    bf16* out0 = a.out + (static_cast<size_t>(b) * a.Lq + r0) * 256 + col0 + hl * 32;
-    bf16* out1 = out0 + 8 * 256;
-#pragma unroll
-    for (int n2 = 0; n2 < 4; n2 += 2) {
-      const uint32_t a0 = pack_bf16(o[n2][0] * i0, o[n2][1] * i0), a1 = pack_bf16(o[n2][2] * i1, o[n2][3] * i1);
-      const uint32_t b0 = pack_bf16(o[n2 + 1][0] * i0, o[n2 + 1][1] * i0),
-                     b1 = pack_bf16(o[n2 + 1][2] * i1, o[n2 + 1][3] * i1);
-      // even t keeps n-tile n2 (receives the partner's n2 columns), odd t keeps n-tile n2 + 1
-      const bool odd = t & 1;
-      const uint32_t x0 = __shfl_xor_sync(0xffffffffu, odd ? a0 : b0, 1);
-      const uint32_t x1 = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
-      const int cb = (odd ? n2 + 1 : n2) * 8 + 2 * (t & ~1);    // first of 4 contiguous columns
-      uint2 w0, w1;
-      w0.x = odd ? x0 : a0; w0.y = odd ? b0 : x0;
-      w1.x = odd ? x1 : a1; w1.y = odd ? b1 : x1;
-      if (r0 < a.Lq) *reinterpret_cast<uint2*>(out0 + cb) = w0;
-      if (r1 < a.Lq) *reinterpret_cast<uint2*>(out1 + cb) = w1;
-    }
-    if (a.tsum) {
-      ts0 += __shfl_xor_sync(0xffffffffu, ts0, 1); ts0 += __shfl_xor_sync(0xffffffffu, ts0, 2);
-      ts1 += __shfl_xor_sync(0xffffffffu, ts1, 1); ts1 += __shfl_xor_sync(0xffffffffu, ts1, 2);
-      if (t == 0) {
-        const int h = col0 / 32 + hl;
-        float* ts = a.tsum + static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq;
-        if (r0 < a.Lq) ts[r0] = ts0 * i0;
-        if (r1 < a.Lq) ts[r1] = ts1 * i1;
-      }
-    }
-  };
-
-  int it = 0;
-  if (static_cast<int>(blockIdx.x) < items) stage(blockIdx.x, 0);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-    const int b = item / GROUPS, col0 = (item - b * GROUPS) * (HG * 32);
-    if (item + static_cast<int>(gridDim.x) < items) stage(item + gridDim.x, (it + 1) & 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    uint32_t aq0[2][4], aq1[2][4];
-    const int u0 = warp, u1 = warp + W;
-    if (u0 < units) load_q(b, col0, u0, aq0);
-    if (u1 < units) load_q(b, col0, u1, aq1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();
-    int klen = a.kbase + a.klen_src[b];
-    if (klen > a.Lk) klen = a.Lk;
-    const bf16* sK = sbuf + (it & 1) * BUF;
-    const bf16* sV = KV_SHARED ? sK : sK + LkPad * PITCH;
-    if (u0 < units) compute(b, col0, klen, sK, sV, u0, aq0);
-    if (u1 < units) compute(b, col0, klen, sK, sV, u1, aq1);
-    for (int u = warp + 2 * W; u < units; u += W) {   // longer videos: more than two units per warp
-      load_q(b, col0, u, aq0);
-      compute(b, col0, klen, sK, sV, u, aq0);
-    }
-    __syncthreads();   // everyone is done with this buffer before the next iteration refills it
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-template <int NT, bool KV_SHARED, int HG, int W>
-static int launch_attn_stream(cudaStream_t st, const AttnArgs& a) {
-  constexpr int PITCH = HG * 32 + 8;
-  const size_t smem = static_cast<size_t>(2) * NT * 8 * PITCH * (KV_SHARED ? 1 : 2) * 2;
-  static thread_local bool set = false;
-  if (!set) {
-    FVTG_CUDA_OK(cudaFuncSetAttribute(attn_stream_kernel<NT, KV_SHARED, HG, W>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
-  }
-  const int per_sm = KV_SHARED ? 2 : 4;
-  const int items = a.B * (8 / HG);
-  const int grid = items < sm_count() * per_sm ? items : sm_count() * per_sm;
-  ProfScope prof(st, PC_ATTN);
-  FVTG_CUDA_OK(launch_pdl(attn_stream_kernel<NT, KV_SHARED, HG, W>, dim3(grid), dim3(W * 32), smem, st, a));
-  FVTG_LAUNCH_CHECK("attn_stream_kernel");
-  return FVTG_OK;
-}
-
 template <int NT, bool KV_SHARED>
 static int launch_attn_video(cudaStream_t st, const AttnArgs& a, int LqPad, size_t smem) {
   static thread_local size_t set = 0;
@@ -589,10 +365,6 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
     const bool aligned = (a.ldq % 8 == 0) && (a.ldk % 8 == 0) && (a.ldv % 8 == 0) &&
                          ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) |
                            reinterpret_cast<uintptr_t>(a.v)) & 15) == 0;
-    static const bool stream = [] { const char* e = getenv("FVTG_ATTN_STREAM"); return !e || atoi(e) != 0; }();
-    if (stream && a.Lk <= 80 && aligned && (a.ldq % 2 == 0)) {
-      return shared_kv ? launch_attn_stream<10, true, 4, 10>(st, a) : launch_attn_stream<10, false, 2, 5>(st, a);
-    }
     if (a.Lk <= 160 && smem_v <= 200 * 1024 && aligned) {
       if (nt == 10) return shared_kv ? launch_attn_video<10, true>(st, a, LqPad, smem_v)
                                      : launch_attn_video<10, false>(st, a, LqPad, smem_v);
