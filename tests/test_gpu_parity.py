@@ -72,6 +72,47 @@ def test_gemm_against_torch(lib):
     del C
 
 
+def test_first_projection_kernel_against_torch(lib):
+    """inproj_kernel alone (LayerNorm(raw dim) folded into the GEMM, ReLU, LayerNorm(256)) against an fp64
+    torch restatement: ragged feature dims (tail k-block), row counts off the tile size, features with a
+    large common offset (the per-row shift that keeps the folded LayerNorm's cancellation benign)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for rows, dim, offset in [(300, 770, 0.0), (129, 66, 0.0), (1000, 4096, 0.0), (77, 2818, 0.0),
+                              (20000, 770, 0.0), (513, 4096, 40.0), (256, 514, -25.0)]:
+        dim_pad = (dim + 63) // 64 * 64
+        x = (torch.randn(rows, dim, generator=g) * (1.0 + torch.rand(rows, 1, generator=g)) + offset).to(dev)
+        W = torch.randn(256, dim, generator=g) / dim ** 0.5
+        gamma = 1.0 + 0.2 * torch.randn(dim, generator=g)
+        beta = 0.1 * torch.randn(dim, generator=g)
+        b = 0.1 * torch.randn(256, generator=g)
+        g1 = 1.0 + 0.2 * torch.randn(256, generator=g)
+        b1 = 0.1 * torch.randn(256, generator=g)
+        wg = torch.zeros(256, dim_pad)
+        wg[:, :dim] = W * gamma
+        wg = wg.to(torch.bfloat16)
+        wsum = wg.float().sum(1)
+        cfold = W @ beta + b
+        out = torch.full((rows, 256), float("nan"), device=dev, dtype=torch.bfloat16)
+        t = [v.to(dev).contiguous() for v in (wg, wsum, cfold, g1, b1)]
+        rc = lib.fvtg_dbg_inproj(x.data_ptr(), rows, dim, dim_pad, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                                 t[3].data_ptr(), t[4].data_ptr(), out.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.fvtg_last_error()
+        torch.cuda.synchronize()
+        xd = x.double().cpu()
+        ln = (xd - xd.mean(1, keepdim=True)) / torch.sqrt(xd.var(1, unbiased=False, keepdim=True) + 1e-5)
+        y = torch.relu((ln * gamma.double() + beta.double()) @ W.double().t() + b.double())
+        y = (y - y.mean(1, keepdim=True)) / torch.sqrt(y.var(1, unbiased=False, keepdim=True) + 1e-5)
+        ref = y * g1.double() + b1.double()
+        err = (out.double().cpu() - ref).abs().max().item()
+        assert err <= 3e-2 * max(ref.abs().max().item(), 1.0), (rows, dim, offset, err)   # bf16 operands + output
+    # odd feature dims are rejected, not mis-read
+    bad = lib.fvtg_dbg_inproj(x.data_ptr(), 4, 65, 128, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                              t[3].data_ptr(), t[4].data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert bad != 0
+
+
 @pytest.mark.parametrize("entry", load_forward_index(), ids=lambda e: e["file"][:-4])
 def test_forward_matches_oracle_and_golden(entry):
     from oracle import forward as O
