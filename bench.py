@@ -174,6 +174,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl ours) needs a B200: there is no CPU fallback")
     torch.cuda.set_device(local)
+    from flashvtg_b200.distributed import bind_to_gpu_numa_node
+    saved_affinity = os.sched_getaffinity(0)
+    numa_bound = bind_to_gpu_numa_node(local)   # before any pinned allocation
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -279,7 +282,8 @@ def run_ours(args):
                                                  for v in out_host["o"].values() if torch.is_tensor(v))),
            "api": f"FlashVTGB200.infer_host(chunk_videos={args.e2e_chunk}): pinned host fp32 features -> "
                   "host ranked spans; H2D overlapped with compute on a second stream",
-           "steps": k2, "ms_per_step": ms2 / k2}
+           "steps": k2, "ms_per_step": ms2 / k2,
+           "host_numa_bound": bool(numa_bound)}   # rank pinned to its GPU's local CPUs before allocating
 
     # ---- informational: the same metric fed from RAW half-precision feature arrays (device-resident
     # input pipeline): L2-norm / TEF / padding run on the device, so the feature store
@@ -366,6 +370,7 @@ def run_ours(args):
                 "class_ms_per_step": cls_ms, "class_launches_per_step": cls_ln,
                 "hbm_input_gbs": e2e["h2d_bytes_per_step"] / world / (ms / args.steps * 1e-3) / 1e9}
         # ---- CPU baseline: the oracle port on a bounded sample, on this box's host cores -------
+        os.sched_setaffinity(0, saved_affinity)   # the CPU baseline gets every core back
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

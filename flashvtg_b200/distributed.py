@@ -13,6 +13,31 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index`, so that the pinned
+    host buffers it allocates afterwards (first touch) sit on the socket that GPU's PCIe link hangs off.
+    With one rank per GPU and 8 ranks streaming features over PCIe at once, buffers on the wrong socket
+    share the inter-socket link.  Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates by PCI bus id; CUDA_VISIBLE_DEVICES remapping is resolved through the UUID
+        props = torch.cuda.get_device_properties(device_index)
+        uuid = getattr(props, "uuid", None)
+        handle = None
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:  # noqa: BLE001
+                handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:  # noqa: BLE001 - best effort: affinity is an optimisation, never a requirement
+        return False
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [start, end) slice of n items owned by `rank`: the first n % world ranks get one
     extra item, so shard sizes differ by at most one."""
