@@ -225,7 +225,6 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ I
     const int r = wq * 32 + lane;
     int it = 0;
     uint32_t u[16];
-    float v[16];
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
@@ -236,42 +235,64 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ I
       const uint32_t tacc = tmem_base + acc * 256 + (static_cast<uint32_t>(wq * 32) << 16);
       const float2 st = s_stat[acc * 128 + r];
       const float ms = st.x, rstd = st.y;
-      // pass 1: y = relu(rstd * (acc - ms * wsum) + cfold); LayerNorm(256) statistics; y back into TMEM
-      float shift = 0.f, t1 = 0.f, t2 = 0.f;
+      // pass 1: y = relu(rstd * (acc - ms * wsum) + cfold); LayerNorm(256) statistics; y back into TMEM.
+      // Packed fp32x2 arithmetic: the four epilogue warps are the critical path of short-K tiles.
+      const uint64_t rstd2 = f2_pack(rstd, rstd), k2 = f2_pack(-rstd * ms, -rstd * ms);
+      uint64_t nshift2 = 0ull, t1 = 0ull, t2 = 0ull;
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {
         const int c0 = c * 16;
         tmem_ld16(tacc + c0, u);
         tmem_ld_wait();
+        const uint64_t* ws2 = reinterpret_cast<const uint64_t*>(s_wsum + c0);
+        const uint64_t* cf2 = reinterpret_cast<const uint64_t*>(s_cf + c0);
+        if (c == 0) {
+          const float y0 = fmaxf(fmaf(__uint_as_float(u[0]), rstd, fmaf(-rstd * ms, s_wsum[0], s_cf[0])), 0.f);
+          nshift2 = f2_pack(-y0, -y0);
+        }
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = fmaxf(rstd * (__uint_as_float(u[j]) - ms * s_wsum[c0 + j]) + s_cf[c0 + j], 0.f);
-        if (c == 0) shift = v[0];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float d = v[j] - shift;
-          t1 += d;
-          t2 += d * d;
-          u[j] = __float_as_uint(v[j]);
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t y = f2_fma(f2_pack(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1])), rstd2,
+                                    f2_fma(k2, ws2[j], cf2[j]));
+          float ya, yb;
+          f2_unpack(y, ya, yb);
+          ya = fmaxf(ya, 0.f);
+          yb = fmaxf(yb, 0.f);
+          const uint64_t d = f2_add(f2_pack(ya, yb), nshift2);
+          t1 = f2_add(t1, d);
+          t2 = f2_fma(d, d, t2);
+          u[2 * j] = __float_as_uint(ya);
+          u[2 * j + 1] = __float_as_uint(yb);
         }
         tmem_st16(tacc + c0, u);
       }
       tmem_st_wait();
-      const float mean = shift + t1 * (1.f / 256.f);
-      const float var = fmaxf((t2 - t1 * t1 * (1.f / 256.f)) * (1.f / 256.f), 0.f);
+      float t1a, t1b, t2a, t2b, nsh, nsh_;
+      f2_unpack(t1, t1a, t1b);
+      f2_unpack(t2, t2a, t2b);
+      f2_unpack(nshift2, nsh, nsh_);
+      const float s1 = t1a + t1b, s2 = t2a + t2b;
+      const float mean = s1 * (1.f / 256.f) - nsh;
+      const float var = fmaxf((s2 - s1 * s1 * (1.f / 256.f)) * (1.f / 256.f), 0.f);
       const float rs = rsqrtf(var + 1e-5f);
+      const uint64_t rs2 = f2_pack(rs, rs), nmean2 = f2_pack(-mean, -mean);
       // pass 2: normalise -> bf16 -> 32-byte row stores
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {
         const int c0 = c * 16;
         tmem_ld16(tacc + c0, u);
         tmem_ld_wait();
+        const uint64_t* g2 = reinterpret_cast<const uint64_t*>(s_g1 + c0);
+        const uint64_t* b2 = reinterpret_cast<const uint64_t*>(s_b1 + c0);
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float a = (__uint_as_float(u[2 * j]) - mean) * rs * s_g1[c0 + 2 * j] + s_b1[c0 + 2 * j];
-          const float b = (__uint_as_float(u[2 * j + 1]) - mean) * rs * s_g1[c0 + 2 * j + 1] + s_b1[c0 + 2 * j + 1];
-          w[j] = pack_bf16(a, b);
+          const uint64_t a2 = f2_mul(rs2, g2[j]);
+          const uint64_t o = f2_fma(f2_pack(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1])), a2,
+                                    f2_fma(nmean2, a2, b2[j]));
+          float oa, ob;
+          f2_unpack(o, oa, ob);
+          w[j] = pack_bf16(oa, ob);
         }
         if (row < g.rows) st_global_v8(g.out + static_cast<size_t>(row) * 256 + c0, w);
       }
