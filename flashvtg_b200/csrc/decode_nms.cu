@@ -64,16 +64,34 @@ __device__ void nms_f32_warp(NmsSmem& S, int n, float thd, int mode, int lane) {
     const int r = lane + 32 * h;
     if (r < n) { st[h] = S.st[r]; ed[h] = S.ed[r]; sc[h] = S.sc[r]; sr[h] = S.src[r]; pos[h] = r; }
   }
+  // Everything that does not change inside the serial loop is hoisted: the order-preserving score keys
+  // (recomputed only when a score changes), the window lengths, the guard band of the IoU test.
+  unsigned key[2];
+  float len[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    key[h] = score_key(sc[h]);
+    len[h] = __fsub_rn(ed[h], st[h]);
+  }
+  const float thd_hi = thd * (1.f + 1e-6f), thd_lo = thd * (1.f - 1e-6f);
   for (int i = 0; i < n; ++i) {
+    const unsigned ui = static_cast<unsigned>(i);
+    // NORMAL mode: once every row still in play has score +0 the remaining steps are no-ops (equal keys:
+    // the arg-max is position i itself, the swap is the identity, suppression writes 0 over 0)
+    if (mode == FVTG_NMS_NORMAL) {
+      const bool idle0 = pos[0] == 0xFFFFFFFFu || pos[0] < ui || __float_as_uint(sc[0]) == 0u;
+      const bool idle1 = pos[1] == 0xFFFFFFFFu || pos[1] < ui || __float_as_uint(sc[1]) == 0u;
+      if (__all_sync(FULL, idle0 && idle1)) break;
+    }
     // first argmax over positions [i, n): largest key, then smallest position
     unsigned k[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) k[h] = (pos[h] != 0xFFFFFFFFu && pos[h] >= static_cast<unsigned>(i)) ? score_key(sc[h]) : 0u;
+    for (int h = 0; h < 2; ++h) k[h] = (pos[h] != 0xFFFFFFFFu && pos[h] >= ui) ? key[h] : 0u;
     const unsigned kmax = __reduce_max_sync(FULL, k[0] > k[1] ? k[0] : k[1]);
     unsigned cand = 0xFFFFFFFFu;
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      if (pos[h] != 0xFFFFFFFFu && pos[h] >= static_cast<unsigned>(i) && k[h] == kmax && pos[h] < cand) cand = pos[h];
+      if (pos[h] != 0xFFFFFFFFu && pos[h] >= ui && k[h] == kmax && pos[h] < cand) cand = pos[h];
     const unsigned bpos = __reduce_min_sync(FULL, cand);   // position of the selected row
     // the selected row's window, broadcast from its owner; then the swap of positions i <-> bpos
     unsigned sb = 0u, eb = 0u;
@@ -84,23 +102,30 @@ __device__ void nms_f32_warp(NmsSmem& S, int n, float thd, int mode, int lane) {
     const float e0 = __uint_as_float(__reduce_or_sync(FULL, eb));
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (pos[h] == bpos) pos[h] = i;
-      else if (pos[h] == static_cast<unsigned>(i)) pos[h] = bpos;
+      if (pos[h] == bpos) pos[h] = ui;
+      else if (pos[h] == ui) pos[h] = bpos;
     }
     // suppression of the rows behind position i against the selected row
     const float a0 = __fsub_rn(e0, s0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (pos[h] != 0xFFFFFFFFu && pos[h] > static_cast<unsigned>(i)) {
-        const float a1 = __fsub_rn(ed[h], st[h]);
+      if (pos[h] != 0xFFFFFFFFu && pos[h] > ui) {
         float inter = __fsub_rn(fminf(e0, ed[h]), fmaxf(s0, st[h]));
         if (inter < 0.f) inter = 0.f;  // clamp(min=0), NaN stays NaN
-        const float uni = __fsub_rn(__fadd_rn(a0, a1), inter);
-        const float iou = __fdiv_rn(inter, uni);
+        const float uni = __fsub_rn(__fadd_rn(a0, len[h]), inter);
         if (mode == FVTG_NMS_NORMAL) {
-          if (iou >= thd) sc[h] = 0.f;  // NaN compares false: kept
+          // iou >= thd with the IEEE division only inside a +-1e-6 band around the threshold (and for
+          // NaN): the fast quotient is within 2 ulp, so outside the band both agree
+          const float qa = __fdividef(inter, uni);
+          bool sup;
+          if (qa > thd_hi) sup = true;
+          else if (qa < thd_lo) sup = false;
+          else sup = __fdiv_rn(inter, uni) >= thd;   // NaN compares false: kept
+          if (sup) { sc[h] = 0.f; key[h] = 0x80000000u; }
         } else {
+          const float iou = __fdiv_rn(inter, uni);
           sc[h] = __fmul_rn(sc[h], __fsub_rn(1.f, iou));
+          key[h] = score_key(sc[h]);
         }
       }
     }
@@ -246,28 +271,45 @@ decode_nms_kernel(const FvtgDecodeParams p, const int Lv, const int n_max, const
   }
   __syncthreads();
   DEC_TRACE(1);
-  // bitonic sort, descending
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < npow2; i += DEC_THREADS) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], c = keys[ixj];
-          const bool desc = (i & k) == 0;
-          if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+  const int topk = p.topk;
+  const int top = N < topk ? N : topk;
+  const unsigned long long* top_keys = keys;
+  if (N <= 512) {
+    // Few candidates (155 points for a 75-clip video): rank by counting instead of a bitonic network -
+    // one pass of N broadcast reads per key and ONE barrier instead of 36 barrier-separated stages.
+    // Keys are unique (the point index is part of the key), so ranks are a permutation.
+    unsigned long long* tk = reinterpret_cast<unsigned long long*>(
+        dec_smem + static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES + sizeof(HullSmem));
+    for (int n = tid; n < N; n += DEC_THREADS) {
+      const unsigned long long key = keys[n];
+      int rank = 0;
+      for (int m = 0; m < N; ++m) rank += keys[m] > key;
+      if (rank < top) tk[rank] = key;
+    }
+    __syncthreads();
+    top_keys = tk;
+  } else {
+    // bitonic sort, descending
+    for (int k = 2; k <= npow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < npow2; i += DEC_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = keys[i], c = keys[ixj];
+            const bool desc = (i & k) == 0;
+            if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   DEC_TRACE(2);
-  const int topk = p.topk;
-  const int top = N < topk ? N : topk;
   const float dur = duration ? duration[b] : 3.0e38f;
   if (tid < NMS_MAX) {
     float st = 0.f, ed = 0.f, sc = 0.f;
     if (tid < top) {
-      const unsigned long long key = keys[tid];
+      const unsigned long long key = top_keys[tid];
       const int n = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFull));
       sc = __uint_as_float(static_cast<unsigned>(key >> 32));
       int l = 0;
@@ -389,7 +431,7 @@ int launch_decode_nms(cudaStream_t st, const FvtgDecodeParams& p, int B, int Lv,
     return fail(FVTG_EINVAL, "decode: unknown nms_mode %d", p.nms_mode);
   int npow2 = 64;
   while (npow2 < n_max) npow2 <<= 1;
-  const size_t smem = static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES + sizeof(HullSmem);
+  const size_t smem = static_cast<size_t>(npow2) * 8 + DEC_NMS_BYTES + sizeof(HullSmem) + NMS_MAX * 8 /*top keys*/;
   ProfScope prof(st, PC_DECODE);
   decode_nms_kernel<<<B, DEC_THREADS, smem, st>>>(p, Lv, n_max, npow2, cls, conf, coord, vlen,
                                                    duration, out, dbg_trace());
