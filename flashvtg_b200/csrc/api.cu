@@ -347,9 +347,7 @@ static int pyramid_heads_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeig
                                int B, int Lv, const float* F, bool f_blocked, const int* vlen,
                                float* cls, float* conf, float* coord) {
   PyrGeo geo = make_geo(c, Lv, vlen);
-  FVTG_CUDA_OK(cudaMemsetAsync(w.H1, 0, static_cast<size_t>(B) * geo.PH1 * 256 * sizeof(bf16), st));
-  FVTG_CUDA_OK(cudaMemsetAsync(w.H2, 0, static_cast<size_t>(B) * geo.PH2 * 256 * sizeof(bf16), st));
-  count_launch(2);
+  // level0 also zeroes the rows of H1 / H2 that no producer writes (pads, positions past a video's length)
   FVTG_TRY(launch_level0(st, F, w.chain0, w.H1, w.H2, B, Lv, geo, f_blocked));
   // Temporal Feature Layering (blocks.py:52-70): level l = l strided convs from ReLU(F), own weights
   for (int l = 1; l < geo.nlev; ++l) {

@@ -140,6 +140,50 @@ __global__ void level0_kernel(const float* __restrict__ F, bf16* __restrict__ ch
     *reinterpret_cast<uint4*>(H1 + r1 * 256 + c8) = o;
     *reinterpret_cast<uint4*>(H2 + r2 * 256 + c8) = o;
   }
+  // The rows of H1 / H2 that NO producer ever writes - the pad rows around and between the levels, the
+  // positions past this video's length in every level, the tail of the packed H2 row space - must read
+  // as zero for the conv taps.  They are few (12 of 294 rows for a full-length 75-clip video), so the
+  // threads of this video's first chain rows zero them here instead of two 77 MB memsets per forward.
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  int nvalid = 0;
+#pragma unroll
+  for (int l = 0; l < FVTG_MAX_LEVELS; ++l) nvalid += l < geo.nlev ? vl >> l : 0;   // static indices: geo stays in param space
+  const int nzero = (geo.PH1 - nvalid) + (geo.PH2 - nvalid);   // rows of this video nobody writes
+  for (int k = i; k < nzero; k += geo.P0) {
+    int q = k;
+    bool done = false;
+    // H1 segments: leading pad, then after every level's valid rows up to the next level's first row
+    if (q < geo.pad) {
+      *reinterpret_cast<uint4*>(H1 + (static_cast<size_t>(b) * geo.PH1 + q) * 256 + c8) = z;
+      continue;
+    }
+    q -= geo.pad;
+#pragma unroll
+    for (int l = 0; l < FVTG_MAX_LEVELS; ++l) {
+      if (l >= geo.nlev || done) continue;
+      const int start = geo.o1[l] + (vl >> l);
+      const int end = (l + 1 < FVTG_MAX_LEVELS && l + 1 < geo.nlev) ? geo.o1[l + 1 < FVTG_MAX_LEVELS ? l + 1 : l] : geo.PH1;
+      if (q < end - start) {
+        *reinterpret_cast<uint4*>(H1 + (static_cast<size_t>(b) * geo.PH1 + start + q) * 256 + c8) = z;
+        done = true;
+      } else {
+        q -= end - start;
+      }
+    }
+    if (done) continue;
+    // H2 segments: leading pad, then everything behind the packed valid rows
+    if (q < geo.pad) {
+      *reinterpret_cast<uint4*>(H2 + (static_cast<size_t>(b) * geo.PH2 + q) * 256 + c8) = z;
+      continue;
+    }
+    q -= geo.pad;
+    const int tail0 = geo.pad + nvalid;
+    if (q < geo.PH2 - tail0) {
+      *reinterpret_cast<uint4*>(H2 + (static_cast<size_t>(b) * geo.PH2 + tail0 + q) * 256 + c8) = z;
+      continue;
+    }
+    break;
+  }
 }
 
 int launch_level0(cudaStream_t st, const float* F, bf16* chain0, bf16* H1, bf16* H2, int B, int Lv,
