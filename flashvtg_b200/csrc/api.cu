@@ -57,7 +57,7 @@ struct Ws {
   bf16 *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
   float *Xf, *Yf, *pos_v, *pos_d, *tsum, *sal_scratch;
   // pyramid + heads
-  bf16 *chain0, *chainA, *chainB, *H1, *H2, *hA, *hB, *mA, *mB;
+  bf16 *chain0, *chainA[FVTG_MAX_LEVELS], *chainB[FVTG_MAX_LEVELS], *H1, *H2, *hA, *hB, *mA, *mB;
   // per-chunk head logits when the caller does not want them
   float *cls, *conf, *coord;
   size_t h1_rows, h2_rows;
@@ -87,8 +87,16 @@ static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws*
   t.sal_scratch = k.take<float>(static_cast<size_t>(Bc) * 513 + 64);
   const size_t Rc = static_cast<size_t>(Bc) * g.P0;
   t.chain0 = k.take<bf16>(Rc * 256);
-  t.chainA = k.take<bf16>(Rc / 2 * 256 + 256);
-  t.chainB = k.take<bf16>(Rc / 4 * 256 + 256);
+  // pyramid chains run level-parallel (one grouped launch per step), so every level >= 2 keeps its own
+  // ping-pong pair: A for odd steps (<= Rc / 2 rows), B for even steps (<= Rc / 4 rows)
+  for (int l = 0; l < FVTG_MAX_LEVELS; ++l) {
+    t.chainA[l] = nullptr;
+    t.chainB[l] = nullptr;
+    if (l >= 2 && l < g.nlev) {
+      t.chainA[l] = k.take<bf16>(Rc / 2 * 256 + 256);
+      t.chainB[l] = k.take<bf16>(Rc / 4 * 256 + 256);
+    }
+  }
   t.h1_rows = static_cast<size_t>(Bc) * g.PH1;
   t.h2_rows = static_cast<size_t>(Bc) * g.PH2;
   const size_t Rh = t.h1_rows > t.h2_rows ? t.h1_rows : t.h2_rows;
@@ -349,11 +357,16 @@ static int pyramid_heads_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeig
   PyrGeo geo = make_geo(c, Lv, vlen);
   // level0 also zeroes the rows of H1 / H2 that no producer writes (pads, positions past a video's length)
   FVTG_TRY(launch_level0(st, F, w.chain0, w.H1, w.H2, B, Lv, geo, f_blocked));
-  // Temporal Feature Layering (blocks.py:52-70): level l = l strided convs from ReLU(F), own weights
-  for (int l = 1; l < geo.nlev; ++l) {
-    const bf16* src = w.chain0;
-    bf16* pp[2] = {w.chainA, w.chainB};
-    for (int j = 1; j <= l; ++j) {
+  // Temporal Feature Layering (blocks.py:52-70): level l = l strided convs from ReLU(F), own weights.
+  // The chains of different levels are independent, so step j of every level l >= j goes out as ONE
+  // grouped launch (4 + 3 + 2 + 1 GEMMs in 4 launches instead of 10; the level-parallel CTAs also share
+  // the step-1 input through L2).  FVTG_PYR_GROUP=0 restores one launch per (level, step).
+  static const bool grouped = [] { const char* e = getenv("FVTG_PYR_GROUP"); return !e || atoi(e) != 0; }();
+  for (int j = 1; j < geo.nlev; ++j) {
+    GemmOperands ops[FVTG_MAX_LEVELS];
+    GemmArgs ga[FVTG_MAX_LEVELS];
+    int n = 0;
+    for (int l = j; l < geo.nlev; ++l) {
       const int rows_out = B * (geo.P0 >> j);
       GemmArgs g = gemm_args(rows_out, 256, 256, 512);
       g.epi.mode = EPI_ROW;
@@ -363,11 +376,21 @@ static int pyramid_heads_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeig
       g.epi.bias = W.pyr[l][j - 1].conv.b;
       g.epi.gamma = W.pyr[l][j - 1].ln.g; g.epi.beta = W.pyr[l][j - 1].ln.b;
       g.epi.post_relu = 1;
-      bf16* dst = pp[(j - 1) & 1];
+      const bf16* src = (j == 1) ? w.chain0 : (((j - 1) & 1) ? w.chainA[l] : w.chainB[l]);
+      bf16* dst = (j & 1) ? w.chainA[l] : w.chainB[l];
       g.epi.out_bf16 = (j == l) ? nullptr : dst;
       g.epi.out_x1 = w.H1; g.epi.out_x2 = w.H2;
-      FVTG_TRY(launch_gemm(st, src, nullptr, rows_out, 512, 512, W.pyr[l][j - 1].conv.w, g));
-      src = dst;
+      ops[n].a = src; ops[n].a2 = nullptr;
+      ops[n].a_rows = rows_out; ops[n].a_cols = 512; ops[n].a_pitch = 512;
+      ops[n].w = W.pyr[l][j - 1].conv.w;
+      ga[n] = g;
+      ++n;
+    }
+    if (grouped && n <= 4) {
+      FVTG_TRY(launch_gemm_group(st, n, ops, ga));
+    } else {
+      for (int i = 0; i < n; ++i)
+        FVTG_TRY(launch_gemm(st, ops[i].a, nullptr, ops[i].a_rows, 512, 512, ops[i].w, ga[i]));
     }
   }
   FVTG_CUDA_OK(cudaMemsetAsync(cls, 0, sizeof(float) * B * geo.n_max, st));

@@ -131,10 +131,11 @@ __device__ __forceinline__ void act32(float* v, int act, float slope) {
 
 __device__ __forceinline__ void gemm_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-            const __grid_constant__ GemmArgs g) {
+// The whole kernel as a device function of ONE problem (tensor maps + arguments living in kernel
+// parameter space): gemm_kernel runs it for its single problem, gemm_group_kernel lets blockIdx.y pick
+// one of up to four independent problems that then share the SMs (gridDim.x CTAs each).
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                                          const CUtensorMap& tmOut, const GemmArgs& g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ symbol (an integer round trip
   // would demote every later access to a generic LD/ST)
@@ -460,9 +461,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows, uint64_t a_cols,
-                uint64_t a_pitch, const void* w, const GemmArgs& args) {
-  if (args.M <= 0) return FVTG_OK;
+struct GemmProblem {
+  CUtensorMap tmA, tmA2, tmB, tmOut;
+  GemmArgs g;
+};
+constexpr int GEMM_MAX_GROUP = 4;
+struct GemmGroup {
+  GemmProblem p[GEMM_MAX_GROUP];
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+            const __grid_constant__ GemmArgs g) {
+  gemm_body(tmA, tmA2, tmB, tmOut, g);
+}
+
+// Independent small GEMMs in one launch (the pyramid steps of different levels): each problem gets
+// gridDim.x persistent CTAs.  The switch keeps every problem's parameter offsets static.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_group_kernel(const __grid_constant__ GemmGroup grp) {
+  switch (blockIdx.y) {
+    case 0: gemm_body(grp.p[0].tmA, grp.p[0].tmA2, grp.p[0].tmB, grp.p[0].tmOut, grp.p[0].g); break;
+    case 1: gemm_body(grp.p[1].tmA, grp.p[1].tmA2, grp.p[1].tmB, grp.p[1].tmOut, grp.p[1].g); break;
+    case 2: gemm_body(grp.p[2].tmA, grp.p[2].tmA2, grp.p[2].tmB, grp.p[2].tmOut, grp.p[2].g); break;
+    default: gemm_body(grp.p[3].tmA, grp.p[3].tmA2, grp.p[3].tmB, grp.p[3].tmOut, grp.p[3].g); break;
+  }
+}
+
+static int gemm_check(const GemmArgs& args) {
   if (args.BN != 256 && args.BN != 128 && args.BN != 16)
     return fail(FVTG_EINVAL, "gemm: unsupported BN %d", args.BN);
   if (args.N % args.BN || args.N > 1024) return fail(FVTG_EINVAL, "gemm: bad N %d", args.N);
@@ -474,17 +501,15 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
     return fail(FVTG_EINVAL, "gemm: EPI_DOT needs N == BN == 128");
   if (args.epi.mode == EPI_COORD && (args.BN != 16 || args.N != 16))
     return fail(FVTG_EINVAL, "gemm: EPI_COORD needs N == BN == 16");
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    FVTG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      GEMM_SMEM_BYTES));
-    attr_set = true;
-  }
-  CUtensorMap ta, ta2, tb, to;
-  FVTG_TRY(make_tmap_bf16(&ta, a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
-  FVTG_TRY(make_tmap_bf16(&ta2, a2 ? a2 : a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
+  return FVTG_OK;
+}
+
+static int gemm_build(GemmProblem* P, const void* a, const void* a2, uint64_t a_rows, uint64_t a_cols,
+                      uint64_t a_pitch, const void* w, const GemmArgs& args) {
+  FVTG_TRY(make_tmap_bf16(&P->tmA, a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
+  FVTG_TRY(make_tmap_bf16(&P->tmA2, a2 ? a2 : a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
   const uint64_t ktot = static_cast<uint64_t>(args.ntaps) * args.kb_per_tap * GEMM_BK;
-  FVTG_TRY(make_tmap_bf16(&tb, w, args.N, ktot, ktot, args.BN, GEMM_BK));
+  FVTG_TRY(make_tmap_bf16(&P->tmB, w, args.N, ktot, ktot, args.BN, GEMM_BK));
   {  // bf16 tile output leaving through the staging tile + TMA store (rows >= M are clipped)
     const GemmEpi& e = args.epi;
     const void* optr = w;
@@ -494,13 +519,59 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
     } else if (e.mode == EPI_ROW && e.out_bf16 && (e.rowmap == RM_NONE || e.rowmap == RM_CHAIN)) {
       optr = e.out_bf16; ocols = 256; opitch = 256; orows = args.M;
     }
-    FVTG_TRY(make_tmap_bf16(&to, optr, orows, ocols, opitch, GEMM_BM, GEMM_BK));
+    FVTG_TRY(make_tmap_bf16(&P->tmOut, optr, orows, ocols, opitch, GEMM_BM, GEMM_BK));
   }
+  P->g = args;
+  return FVTG_OK;
+}
+
+int launch_gemm_group(cudaStream_t st, int n, const GemmOperands* ops, const GemmArgs* args) {
+  if (n < 1 || n > GEMM_MAX_GROUP) return fail(FVTG_EINVAL, "gemm group: 1..%d problems", GEMM_MAX_GROUP);
+  if (n == 1)
+    return launch_gemm(st, ops[0].a, ops[0].a2, ops[0].a_rows, ops[0].a_cols, ops[0].a_pitch, ops[0].w, args[0]);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    FVTG_CUDA_OK(cudaFuncSetAttribute(gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GEMM_SMEM_BYTES));
+    attr_set = true;
+  }
+  GemmGroup grp;
+  memset(&grp, 0, sizeof(grp));
+  int max_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    if (args[i].M <= 0) return fail(FVTG_EINVAL, "gemm group: empty problem");
+    FVTG_TRY(gemm_check(args[i]));
+    FVTG_TRY(gemm_build(&grp.p[i], ops[i].a, ops[i].a2, ops[i].a_rows, ops[i].a_cols, ops[i].a_pitch, ops[i].w,
+                        args[i]));
+    const int tiles = ((args[i].M + GEMM_BM - 1) / GEMM_BM) * (args[i].N / args[i].BN);
+    if (tiles > max_tiles) max_tiles = tiles;
+  }
+  int per = sm_count() / n;
+  if (per > max_tiles) per = max_tiles;
+  ProfScope prof(st, PC_GEMM);
+  FVTG_CUDA_OK(launch_pdl(gemm_group_kernel, dim3(per, n), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, st, grp));
+  FVTG_LAUNCH_CHECK("gemm_group_kernel");
+  return FVTG_OK;
+}
+
+int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows, uint64_t a_cols,
+                uint64_t a_pitch, const void* w, const GemmArgs& args) {
+  if (args.M <= 0) return FVTG_OK;
+  FVTG_TRY(gemm_check(args));
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    FVTG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GEMM_SMEM_BYTES));
+    attr_set = true;
+  }
+  GemmProblem P;
+  FVTG_TRY(gemm_build(&P, a, a2, a_rows, a_cols, a_pitch, w, args));
   const int m_tiles = (args.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = m_tiles * (args.N / args.BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(st, PC_GEMM);
-  FVTG_CUDA_OK(launch_pdl(gemm_kernel, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, st, ta, ta2, tb, to, args));
+  FVTG_CUDA_OK(launch_pdl(gemm_kernel, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, st, P.tmA, P.tmA2, P.tmB,
+                          P.tmOut, P.g));
   FVTG_LAUNCH_CHECK("gemm_kernel");
   return FVTG_OK;
 }

@@ -89,6 +89,15 @@ struct GemmArgs {
 int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows, uint64_t a_cols,
                 uint64_t a_pitch, const void* w, const GemmArgs& args);
 
+// Up to 4 independent GEMMs in ONE launch; problem i runs on its own sm_count / n persistent CTAs.
+struct GemmOperands {
+  const void* a;
+  const void* a2;
+  uint64_t a_rows, a_cols, a_pitch;
+  const void* w;
+};
+int launch_gemm_group(cudaStream_t st, int n, const GemmOperands* ops, const GemmArgs* args);
+
 inline GemmArgs gemm_args(int M, int N, int BN, int K) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
