@@ -488,3 +488,62 @@ def test_uniform_length_hint_changes_nothing():
             outs.append(r)
         for name in ("saliency", "t2vattn", "cls_logit", "conf_logit", "coord", "boundary", "nms_windows"):
             assert torch.equal(getattr(outs[0], name), getattr(outs[1], name)), (lv_true, name)
+
+
+def test_workspace_reuse_across_lengths_leaves_no_stale_rows():
+    """The pyramid row spaces (H1 / H2) are no longer cleared per forward: the level-0 kernel zeroes exactly the
+    rows no producer writes.  A model whose workspace just held full-length videos must give, on a ragged
+    batch, bit-identical results to a fresh model (stale rows of the longer videos would leak into the conv
+    taps), and the grouped pyramid launches must equal the one-launch-per-step schedule."""
+    import subprocess
+    import sys
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS
+    from flashvtg_b200.model import FlashVTGB200
+    cfg = PRESETS["qvh_iv2"]
+    dev = torch.device("cuda:0")
+    sd = synth.make_state_dict(cfg, 2025, spread=True)
+    full = synth.make_inputs(cfg, 12, 75, 32, seed=5)
+    rag = synth.make_inputs(cfg, 12, 75, 32, seed=6, ragged=True, min_lv=3)
+
+    def run(m, b):
+        r = m.infer(b["src_vid"].to(dev), b["vid_len"].to(dev), b["src_txt"].to(dev), b["txt_len"].to(dev),
+                    duration=b["duration"].to(dev), want_heads=True)
+        torch.cuda.synchronize()
+        return {k: getattr(r, k).clone() for k in ("saliency", "cls_logit", "conf_logit", "coord", "boundary", "count")}
+
+    used = FlashVTGB200(cfg).eval()
+    used.load_state_dict(sd)
+    run(used, full)
+    run(used, full)
+    got = run(used, rag)
+    fresh = FlashVTGB200(cfg).eval()
+    fresh.load_state_dict(sd)
+    ref = run(fresh, rag)
+    for k in got:
+        assert torch.equal(got[k], ref[k]), k
+    # grouped vs per-step pyramid launches (separate process: the switch is read once)
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from flashvtg_b200 import synth
+from flashvtg_b200.config import PRESETS
+from flashvtg_b200.model import FlashVTGB200
+cfg = PRESETS["qvh_iv2"]
+m = FlashVTGB200(cfg).eval(); m.load_state_dict(synth.make_state_dict(cfg, 2025, spread=True))
+b = synth.make_inputs(cfg, 12, 75, 32, seed=6, ragged=True, min_lv=3)
+dev = torch.device("cuda:0")
+r = m.infer(b["src_vid"].to(dev), b["vid_len"].to(dev), b["src_txt"].to(dev), b["txt_len"].to(dev),
+            duration=b["duration"].to(dev), want_heads=True)
+torch.save({"cls": r.cls_logit.cpu(), "conf": r.conf_logit.cpu(), "coord": r.coord.cpu()}, sys.argv[1])
+''' % ROOT
+    import tempfile
+    outs = []
+    for grp in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=dict(os.environ, FVTG_PYR_GROUP=grp),
+                           timeout=300)
+            outs.append(torch.load(f.name))
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert torch.equal(outs[1]["cls"], ref["cls_logit"].cpu())
