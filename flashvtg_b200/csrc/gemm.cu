@@ -134,19 +134,28 @@ __device__ __forceinline__ void gemm_epi_bar() { asm volatile("bar.sync 1, 512;"
 // The whole kernel as a device function of ONE problem (tensor maps + arguments living in kernel
 // parameter space): gemm_kernel runs it for its single problem, gemm_group_kernel lets blockIdx.y pick
 // one of up to four independent problems that then share the SMs (gridDim.x CTAs each).
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) share every MMA (cta_group::2, M = 256): each
+// stages its own 128 A rows and HALF of the weight tile, so the weight traffic out of L2 - which bounds
+// the long-K GEMMs (7.8 TB/s of L2 reads for the K = 768 head convs) - is halved.
+template <bool PAIR>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                                           const CUtensorMap& tmOut, const GemmArgs& g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ symbol (an integer round trip
   // would demote every later access to a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // a CTA of a pair stages only half of every weight tile: 32 KB stages, and four of them fit where the
+  // single CTA keeps three 48 KB stages - one more k-block of prefetch depth on a latency-bound pipeline
+  constexpr int NSTAGE = PAIR ? 4 : GEMM_STAGES;
+  constexpr int STAGE_BYTES = PAIR ? GEMM_A_BYTES + GEMM_B_BYTES_MAX / 2 : GEMM_STAGE_BYTES;
+  static_assert(NSTAGE * STAGE_BYTES <= GEMM_STAGES * GEMM_STAGE_BYTES, "stage ring outgrew its region");
   uint8_t* stage_out = smem + GEMM_STAGES * GEMM_STAGE_BYTES;  // 4 swizzled [128][64] bf16 units
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + GEMM_OUT_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + GEMM_STAGES;
-  uint64_t* tfull = bars + 2 * GEMM_STAGES;
-  uint64_t* tempty = bars + 2 * GEMM_STAGES + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+  uint64_t* empty = bars + NSTAGE;
+  uint64_t* tfull = bars + 2 * NSTAGE;
+  uint64_t* tempty = bars + 2 * NSTAGE + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
   float* s_bias = reinterpret_cast<float*>(stage_out + GEMM_OUT_BYTES + 256);
   float* s_gamma = s_bias + 1024;
   float* s_beta = s_gamma + 256;
@@ -158,8 +167,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   const int BN = g.BN;
   const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = g.N / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int total_kb = g.ntaps * g.kb_per_tap;
+  // work items: (m-tile, n-tile), or (pair of m-tiles, n-tile) for a CTA pair; rank = CTA within the pair
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int num_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int first_tile = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -169,19 +182,24 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     prefetch_tmap(&tmOut);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 16);
+      mbar_init(&tempty[a], PAIR ? 32 : 16);   // epilogue warps of both CTAs arrive at the leader
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_holder, 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_cg2(tmem_holder, 512);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_holder, 512);
+      tmem_relinquish();
+    }
   }
   if (warp >= 4) {
     const GemmEpi& e = g.epi;
@@ -199,30 +217,43 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   pdl_wait();   // everything above touched only constants / on-chip state
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer --
+    // PAIR: runs in both CTAs; each loads its own A rows and its half of the weight tile into its own
+    // shared memory, all completion bytes are posted to the LEADER's full barrier.
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = GEMM_A_BYTES + BN * GEMM_BK * 2;
+      const uint32_t b_bytes = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
+      const uint32_t tx = (GEMM_A_BYTES + b_bytes) * (PAIR ? 2 : 1);
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+        const int mt = PAIR ? 2 * mp + static_cast<int>(rank) : mp;   // rows past M are zero-filled by TMA
         GK_TRACE(0, 0);
         const CUtensorMap* ta = (nt >= g.a_switch_ntile) ? &tmA2 : &tmA;
         for (int tap = 0; tap < g.ntaps; ++tap) {
           const int arow = mt * GEMM_BM + g.tap_shift[tap];
           for (int kb = 0; kb < g.kb_per_tap; ++kb) {
             mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* sa = smem + s * GEMM_STAGE_BYTES;
-            mbar_expect_tx(&full[s], tx);
-            tma_load_2d(sa, ta, kb * GEMM_BK, arow, &full[s]);
-            tma_load_2d(sa + GEMM_A_BYTES, &tmB, (tap * g.kb_per_tap + kb) * GEMM_BK, nt * BN,
-                        &full[s]);
-            if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+            uint8_t* sa = smem + s * STAGE_BYTES;
+            if (PAIR) {
+              const uint32_t fb = mapa_u32(&full[s], 0);
+              if (rank == 0) mbar_expect_tx(&full[s], tx);
+              tma_load_2d_cg2(sa, ta, kb * GEMM_BK, arow, fb);
+              tma_load_2d_cg2(sa + GEMM_A_BYTES, &tmB, (tap * g.kb_per_tap + kb) * GEMM_BK,
+                              nt * BN + static_cast<int>(rank) * (BN / 2), fb);
+            } else {
+              mbar_expect_tx(&full[s], tx);
+              tma_load_2d(sa, ta, kb * GEMM_BK, arow, &full[s]);
+              tma_load_2d(sa + GEMM_A_BYTES, &tmB, (tap * g.kb_per_tap + kb) * GEMM_BK, nt * BN,
+                          &full[s]);
+            }
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
         }
         GK_TRACE(0, 1);
@@ -230,12 +261,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer --
-    if (lane == 0) {
+    // PAIR: the leader CTA alone issues, every instruction an M = 256 MMA over both CTAs' tiles
+    if (lane == 0 && (!PAIR || rank == 0)) {
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN);
+      const uint16_t both = 3;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t accph = (it >> 1) & 1;
         GK_TRACE(1, 0);
@@ -246,16 +279,20 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * GEMM_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sa + GEMM_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);
-          if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (PAIR) umma_bf16_cg2(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_cg2(&empty[s], both);
+          else umma_commit(&empty[s]);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (PAIR) umma_commit_cg2(&tfull[acc], both);
+        else umma_commit(&tfull[acc]);
         GK_TRACE(1, 2);
       }
     }
@@ -273,8 +310,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     const bool staged = (e.mode == EPI_TILE) ||
                         (e.mode == EPI_ROW && e.out_bf16 && (e.rowmap == RM_NONE || e.rowmap == RM_CHAIN));
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = PAIR ? 2 * mp + static_cast<int>(rank) : mp;
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
       const int row = mt * GEMM_BM + r;
@@ -447,7 +485,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+        else mbar_arrive(&tempty[acc]);
+      }
       if (leader) GK_TRACE(2, 4);
     }
     if (staged && leader) tma_store_wait_all();
@@ -455,9 +496,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer may still read this CTA's half of B / signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_cg2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -474,7 +517,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
             const __grid_constant__ GemmArgs g) {
-  gemm_body(tmA, tmA2, tmB, tmOut, g);
+  gemm_body<false>(tmA, tmA2, tmB, tmOut, g);
+}
+
+// launched as clusters of 2 CTAs; tmB's box is HALF the weight tile (BN / 2 rows)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ GemmArgs g) {
+  gemm_body<true>(tmA, tmA2, tmB, tmOut, g);
 }
 
 // Independent small GEMMs in one launch (the pyramid steps of different levels): each problem gets
@@ -482,10 +533,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_group_kernel(const __grid_constant__ GemmGroup grp) {
   switch (blockIdx.y) {
-    case 0: gemm_body(grp.p[0].tmA, grp.p[0].tmA2, grp.p[0].tmB, grp.p[0].tmOut, grp.p[0].g); break;
-    case 1: gemm_body(grp.p[1].tmA, grp.p[1].tmA2, grp.p[1].tmB, grp.p[1].tmOut, grp.p[1].g); break;
-    case 2: gemm_body(grp.p[2].tmA, grp.p[2].tmA2, grp.p[2].tmB, grp.p[2].tmOut, grp.p[2].g); break;
-    default: gemm_body(grp.p[3].tmA, grp.p[3].tmA2, grp.p[3].tmB, grp.p[3].tmOut, grp.p[3].g); break;
+    case 0: gemm_body<false>(grp.p[0].tmA, grp.p[0].tmA2, grp.p[0].tmB, grp.p[0].tmOut, grp.p[0].g); break;
+    case 1: gemm_body<false>(grp.p[1].tmA, grp.p[1].tmA2, grp.p[1].tmB, grp.p[1].tmOut, grp.p[1].g); break;
+    case 2: gemm_body<false>(grp.p[2].tmA, grp.p[2].tmA2, grp.p[2].tmB, grp.p[2].tmOut, grp.p[2].g); break;
+    default: gemm_body<false>(grp.p[3].tmA, grp.p[3].tmA2, grp.p[3].tmB, grp.p[3].tmOut, grp.p[3].g); break;
   }
 }
 
@@ -505,11 +556,11 @@ static int gemm_check(const GemmArgs& args) {
 }
 
 static int gemm_build(GemmProblem* P, const void* a, const void* a2, uint64_t a_rows, uint64_t a_cols,
-                      uint64_t a_pitch, const void* w, const GemmArgs& args) {
+                      uint64_t a_pitch, const void* w, const GemmArgs& args, bool pair = false) {
   FVTG_TRY(make_tmap_bf16(&P->tmA, a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
   FVTG_TRY(make_tmap_bf16(&P->tmA2, a2 ? a2 : a, a_rows, a_cols, a_pitch, GEMM_BM, GEMM_BK));
   const uint64_t ktot = static_cast<uint64_t>(args.ntaps) * args.kb_per_tap * GEMM_BK;
-  FVTG_TRY(make_tmap_bf16(&P->tmB, w, args.N, ktot, ktot, args.BN, GEMM_BK));
+  FVTG_TRY(make_tmap_bf16(&P->tmB, w, args.N, ktot, ktot, pair ? args.BN / 2 : args.BN, GEMM_BK));
   {  // bf16 tile output leaving through the staging tile + TMA store (rows >= M are clipped)
     const GemmEpi& e = args.epi;
     const void* optr = w;
@@ -564,9 +615,43 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
                                       GEMM_SMEM_BYTES));
     attr_set = true;
   }
+  const int m_tiles = (args.M + GEMM_BM - 1) / GEMM_BM;
+  {  // CTA pairs for the 256-wide tiles of GEMMs tall enough to fill the machine (FVTG_GEMM_PAIR=0: off)
+    static const bool pair_on = [] { const char* e = getenv("FVTG_GEMM_PAIR"); return !e || atoi(e) != 0; }();
+    const int pair_tiles = ((m_tiles + 1) / 2) * (args.N / args.BN);
+    if (pair_on && args.BN == 256 && pair_tiles >= sm_count() / 2) {
+      static thread_local bool pair_attr = false;
+      if (!pair_attr) {
+        FVTG_CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          GEMM_SMEM_BYTES));
+        pair_attr = true;
+      }
+      GemmProblem P;
+      FVTG_TRY(gemm_build(&P, a, a2, a_rows, a_cols, a_pitch, w, args, true));
+      const int clusters = pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * clusters);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = pdl_enabled() ? 2 : 1;
+      ProfScope prof(st, PC_GEMM);
+      FVTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel, P.tmA, P.tmA2, P.tmB, P.tmOut, P.g));
+      FVTG_LAUNCH_CHECK("gemm_pair_kernel");
+      return FVTG_OK;
+    }
+  }
   GemmProblem P;
   FVTG_TRY(gemm_build(&P, a, a2, a_rows, a_cols, a_pitch, w, args));
-  const int m_tiles = (args.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = m_tiles * (args.N / args.BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(st, PC_GEMM);
