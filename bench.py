@@ -342,7 +342,7 @@ def run_ours(args):
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         fl = flops_by_kernel_class(cfg, LV, LT)
         names = {"layer": "layer_kernel (tcgen05/TMEM + TMA: out_proj + LN1 + FFN + LN2 fused)",
-                 "gemm": "gemm_kernel + mlp_chain_kernel (persistent tcgen05/TMEM + TMA GEMMs, fused epilogues; score-head MLP chained in TMEM)",
+                 "gemm": "gemm_kernel / gemm_pair_kernel (cta_group::2) / gemm_group_kernel + mlp_chain_kernel (persistent tcgen05/TMEM + TMA GEMMs, fused epilogues; score-head MLP chained in TMEM)",
                  "attention": "attention_kernel (per video x 4-head group, mma.sync)",
                  "inproj": "inproj_kernel (LayerNorm-folded first projection, fp32 features read once, tcgen05)"}
         cls_ms = {n: ms_c[i] / ksteps for i, n in enumerate(_lib.PROF_CLASSES)}
