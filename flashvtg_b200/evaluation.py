@@ -182,6 +182,47 @@ def pack_submission(submission, ground_truth, clip_length: int = 2):
     return out
 
 
+def pack_ground_truth(ground_truth, qids, clip_length: int = 2, device="cuda"):
+    """Ground-truth rows (jsonl dicts) of the queries `qids`, in that order -> device tensors for
+    `eval_predictions`.  Done once per dataset split; the per-epoch evaluation then needs no host work."""
+    gt_by_qid = {d["qid"]: d for d in ground_truth}
+    rows = [gt_by_qid[q] for q in qids]
+    Q = len(rows)
+    G = max(max(len(g["relevant_windows"]) for g in rows), 1)
+    C_ = max(max(int(g["duration"] / clip_length) for g in rows), 1)
+    gt_win = np.zeros((Q, G, 2))
+    gt_cnt = np.zeros(Q, np.int32)
+    gt_sal = np.zeros((Q, C_, 3), np.uint8)
+    gt_clips = np.zeros(Q, np.int32)
+    for i, g in enumerate(rows):
+        w = np.asarray(g["relevant_windows"], dtype=np.float64).reshape(-1, 2)
+        gt_win[i, :len(w)] = w
+        gt_cnt[i] = len(w)
+        gt_clips[i] = int(g["duration"] / clip_length)
+        if len(g.get("relevant_clip_ids", [])):
+            gt_sal[i, np.asarray(g["relevant_clip_ids"])] = np.asarray(g["saliency_scores"], np.uint8)
+    return {k: torch.from_numpy(v).to(device) for k, v in
+            dict(gt_win=gt_win, gt_cnt=gt_cnt, gt_sal=gt_sal, gt_clips=gt_clips).items()}
+
+
+def eval_predictions(windows: torch.Tensor, counts: torch.Tensor, saliency: Optional[torch.Tensor],
+                     sal_len: Optional[torch.Tensor], gt: dict, round_4dp: bool = True) -> OrderedDict:
+    """Metrics straight from the device-resident outputs of `FlashVTGB200.infer` - ranked windows
+    [Q][P][3] (start, end, score) with their counts, saliency [Q][L] with the clip counts - against
+    `pack_ground_truth(...)`: what `eval_epoch` gets from writing the submission rows and calling
+    `eval_submission` (inference.py:355-385), without the predictions leaving the GPU.  round_4dp applies the
+    submission's 4-decimal rounding of scores and saliency (inference.py:286-290, 318-320) first."""
+    w = windows.to(torch.float64)
+    sal = None if saliency is None else saliency.to(torch.float64)
+    if round_4dp:
+        w = torch.round(w * 1e4) / 1e4
+        if sal is not None:
+            sal = torch.round(sal * 1e4) / 1e4
+    mr, hl = eval_arrays(w, counts, gt["gt_win"], gt["gt_cnt"], sal, sal_len,
+                         gt["gt_sal"] if sal is not None else None, gt["gt_clips"] if sal is not None else None)
+    return format_metrics(mr, hl)
+
+
 def eval_submission(submission, ground_truth, verbose: bool = True, match_number: bool = True,
                     device: str = "cuda"):
     """Same contract as standalone_eval.eval.eval_submission (eval.py:271-345)."""

@@ -158,3 +158,24 @@ def test_eval_submission_dict_api_and_long_videos():
     assert got == exp
     with pytest.raises(AssertionError):
         ev.eval_submission(sub[:-1], gt, verbose=False)
+
+
+@pytest.mark.gpu
+def test_eval_predictions_from_device_tensors_equals_the_row_api():
+    """Device-resident predictions + packed ground truth give the same dict as the jsonl-row API."""
+    from flashvtg_b200 import evaluation as ev
+    a = random_case(9, Q=64)
+    sub, gt = [], []
+    for i in range(len(a["pred_cnt"])):
+        nc = int(a["gt_clips"][i])
+        sub.append({"qid": 7000 + i, "pred_relevant_windows": a["pred_win"][i, :a["pred_cnt"][i]].tolist(),
+                    "pred_saliency_scores": a["pred_sal"][i, :a["pred_sal_len"][i]].tolist()})
+        gt.append({"qid": 7000 + i, "duration": 2 * nc, "relevant_windows": a["gt_win"][i, :a["gt_cnt"][i]].tolist(),
+                   "relevant_clip_ids": list(range(nc)), "saliency_scores": a["gt_sal"][i, :nc].tolist()})
+    exp = flat(json.loads(json.dumps(ev.eval_submission(sub, gt, verbose=False))))
+    dev = "cuda:0"
+    g = ev.pack_ground_truth(gt[::-1], [d["qid"] for d in sub], device=dev)
+    got = ev.eval_predictions(torch.from_numpy(a["pred_win"]).to(dev), torch.from_numpy(a["pred_cnt"]).to(dev),
+                              torch.from_numpy(a["pred_sal"]).to(dev), torch.from_numpy(a["pred_sal_len"]).to(dev),
+                              g, round_4dp=False)
+    assert flat(json.loads(json.dumps(got))) == exp
