@@ -358,6 +358,10 @@ static int launch_attn_video(cudaStream_t st, const AttnArgs& a, int LqPad, size
 int launch_attention(cudaStream_t st, const AttnArgs& a) {
   if (a.B <= 0) return FVTG_OK;
   {
+    static const bool tc = [] { const char* e = getenv("FVTG_ATTN_TC"); return !e || atoi(e) != 0; }();
+    if (tc) return launch_attention_tc(st, a);
+  }
+  {
     const int LqPad = round_up(a.Lq, 16);
     const int nt = a.Lk <= 80 ? 10 : 20;
     const bool shared_kv = (a.k == a.v) && (a.ldk == a.ldv);

@@ -78,6 +78,8 @@ struct AttnArgs {
   long long* trace;         // debug: clock64 stamps of CTA 0 / CTA 1000 at +3072 (fvtg_dbg_set_trace)
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
+// attn_tc.cu: the same contract on tcgen05 / TMEM (one CTA per video x 128-query block x head pair)
+int launch_attention_tc(cudaStream_t st, const AttnArgs& a);
 
 // ---- saliency.cu ---------------------------------------------------------------------------
 // saliency (transformer.py:106-113) + t2vattnvalues finalisation (model.py:215-216).  F is the
