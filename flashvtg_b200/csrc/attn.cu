@@ -4,151 +4,13 @@
 //   adaptive cross-attention : no projections, softmax over [dummies ‖ text] keys, value sum over
 //       the text keys only, per-row probability mass on text accumulated for t2vattnvalues
 //                                                         [crossattention.py:287-396, model.py:215]
-// Sequences are 4..~1000 tokens with head_dim 32 (2-6 % of the FLOPs): legacy warp-level
-// mma.sync m16n8k16 with an online softmax; the dense d_model contractions go through gemm.cu.
+// Sequences of up to 160 keys (head_dim 32, 2-6 % of the FLOPs) run here on warp-level mma.sync
+// m16n8k16 with the whole score row in registers; longer ones go to the tcgen05 kernel of attn_tc.cu
+// (key blocks of 128 in TMEM).  The dense d_model contractions go through gemm.cu / layer.cu.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace fvtg {
-
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_KS = 40;  // smem key row stride (bf16): 32 + 8 pad -> conflict-free fragment loads
-
-__global__ void __launch_bounds__(ATT_THREADS)
-attention_kernel(const AttnArgs a, const int Lkpad) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  bf16* Ks = reinterpret_cast<bf16*>(att_smem);  // [Lkpad][40]
-  const int vs = Lkpad + 8;
-  bf16* Vt = Ks + static_cast<size_t>(Lkpad) * ATT_KS;  // [32][Lkpad + 8]
-  const int b = blockIdx.x >> 3, h = blockIdx.x & 7;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  int klen = a.kbase + a.klen_src[b];
-  if (klen > a.Lk) klen = a.Lk;
-
-  for (int idx = threadIdx.x; idx < Lkpad * 4; idx += ATT_THREADS) {
-    const int j = idx >> 2, sg = idx & 3;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (j < klen) {
-      const size_t r = static_cast<size_t>(b) * a.Lk + j;
-      kv = *reinterpret_cast<const uint4*>(a.k + r * a.ldk + h * 32 + sg * 8);
-      if (j >= a.v_first) vv = *reinterpret_cast<const uint4*>(a.v + r * a.ldv + h * 32 + sg * 8);
-    }
-    *reinterpret_cast<uint4*>(Ks + j * ATT_KS + sg * 8) = kv;
-    const bf16* ve = reinterpret_cast<const bf16*>(&vv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) Vt[(sg * 8 + e) * vs + j] = ve[e];
-  }
-  __syncthreads();
-
-  const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
-  for (int mt = warp; mt * 16 < a.Lq; mt += ATT_THREADS / 32) {
-    const int r0 = mt * 16 + g, r1 = r0 + 8;
-    uint32_t aq[2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const bf16* q0 = a.q + (static_cast<size_t>(b) * a.Lq + r0) * a.ldq + h * 32 + ks * 16 + 2 * t;
-      const bf16* q1 = a.q + (static_cast<size_t>(b) * a.Lq + r1) * a.ldq + h * 32 + ks * 16 + 2 * t;
-      aq[ks][0] = r0 < a.Lq ? *reinterpret_cast<const uint32_t*>(q0) : 0u;
-      aq[ks][1] = r1 < a.Lq ? *reinterpret_cast<const uint32_t*>(q1) : 0u;
-      aq[ks][2] = r0 < a.Lq ? *reinterpret_cast<const uint32_t*>(q0 + 8) : 0u;
-      aq[ks][3] = r1 < a.Lq ? *reinterpret_cast<const uint32_t*>(q1 + 8) : 0u;
-    }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, ts0 = 0.f, ts1 = 0.f;
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
-
-    for (int kc = 0; kc < klen; kc += 64) {
-      float s[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const bf16* kr = Ks + (kc + nt * 8 + g) * ATT_KS + 2 * t;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-          mma16816(s[nt], aq[ks], b0, b1);
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kc + nt * 8 + 2 * t + (e & 1);
-          const float v = key < klen ? s[nt][e] * sc : -INFINITY;
-          s[nt][e] = v;
-          if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
-      const float al0 = exp2f(m0 - n0), al1 = exp2f(m1 - n1);
-      m0 = n0; m1 = n1;
-      float rs0 = 0.f, rs1 = 0.f, rt0 = 0.f, rt1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kc + nt * 8 + 2 * t + (e & 1);
-          const float p = exp2f(s[nt][e] - (e < 2 ? n0 : n1));
-          s[nt][e] = p;
-          if (e < 2) { rs0 += p; if (key >= a.v_first) rt0 += p; }
-          else       { rs1 += p; if (key >= a.v_first) rt1 += p; }
-        }
-      }
-      l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
-      ts0 = ts0 * al0 + rt0; ts1 = ts1 * al1 + rt1;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1;
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-        for (int nt2 = 0; nt2 < 4; ++nt2) {
-          const bf16* vr = Vt + (nt2 * 8 + g) * vs + kc + kk * 16 + 2 * t;
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
-          mma16816(o[nt2], pa, b0, b1);
-        }
-      }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    ts0 += __shfl_xor_sync(0xffffffffu, ts0, 1); ts0 += __shfl_xor_sync(0xffffffffu, ts0, 2);
-    ts1 += __shfl_xor_sync(0xffffffffu, ts1, 1); ts1 += __shfl_xor_sync(0xffffffffu, ts1, 2);
-    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
-    if (r0 < a.Lq) {
-      bf16* dst = a.out + (static_cast<size_t>(b) * a.Lq + r0) * 256 + h * 32 + 2 * t;
-#pragma unroll
-      for (int nt2 = 0; nt2 < 4; ++nt2)
-        *reinterpret_cast<uint32_t*>(dst + nt2 * 8) = pack_bf16(o[nt2][0] * i0, o[nt2][1] * i0);
-      if (a.tsum && t == 0)
-        a.tsum[static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq + r0] = ts0 * i0;
-    }
-    if (r1 < a.Lq) {
-      bf16* dst = a.out + (static_cast<size_t>(b) * a.Lq + r1) * 256 + h * 32 + 2 * t;
-#pragma unroll
-      for (int nt2 = 0; nt2 < 4; ++nt2)
-        *reinterpret_cast<uint32_t*>(dst + nt2 * 8) = pack_bf16(o[nt2][2] * i1, o[nt2][3] * i1);
-      if (a.tsum && t == 0)
-        a.tsum[static_cast<size_t>(h) * a.B * a.Lq + static_cast<size_t>(b) * a.Lq + r1] = ts1 * i1;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Short sequences (everything QVHighlights-sized): one CTA per (video, group of 4 heads), 8 warps =
@@ -235,22 +97,29 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
       mma16816(s[nt], aq[0], kb[0], kb[1]);
       mma16816(s[nt], aq[1], kb[2], kb[3]);
     }
-    // Key rows >= klen are zero in shared memory, so their scores are exactly 0: the stabilising
-    // offset may include them (softmax is shift invariant) and needs no masking; their probabilities
-    // are forced to 0 below with two compares per tile against this lane's column limit - branch-free,
-    // no per-tile control flow for the register allocator to patch up with moves.
-    float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), 0.f), mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), 0.f);
+    // The stabilising offset is the maximum over the VALID keys only (a row whose valid scores all sit
+    // far below zero must not be flushed by the zero scores of the padded key rows).  Whether a key tile
+    // lies below klen is warp-uniform, so only the tile that straddles klen pays for selects; the
+    // probabilities of padded keys are forced to 0 below with two compares per tile against this lane's
+    // column limit - branch-free, no per-tile control flow in the exp loop.
+    const int lim = klen - 2 * t;          // column c of tile nt is a valid key  <=>  nt * 8 + c < lim
+    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 1; nt < NT; ++nt) {
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 + 8 <= klen) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      } else if (nt * 8 < klen) {
+        const bool k0 = nt * 8 < lim, k1 = nt * 8 + 1 < lim;
+        mx0 = fmaxf(mx0, fmaxf(k0 ? s[nt][0] : -INFINITY, k1 ? s[nt][1] : -INFINITY));
+        mx1 = fmaxf(mx1, fmaxf(k0 ? s[nt][2] : -INFINITY, k1 ? s[nt][3] : -INFINITY));
+      }
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float off0 = mx0 * sc, off1 = mx1 * sc;
-    const int lim = klen - 2 * t;          // column c of tile nt is a valid key  <=>  nt * 8 + c < lim
+    const float off0 = (mx0 == -INFINITY ? 0.f : mx0) * sc, off1 = (mx1 == -INFINITY ? 0.f : mx1) * sc;
     const int vlim = a.v_first - 2 * t;    // ... carries a value              <=>  nt * 8 + c >= vlim
     float l0 = 0.f, l1 = 0.f, ts0 = 0.f, ts1 = 0.f;
     if (a.v_first > 0) {
@@ -358,8 +227,9 @@ static int launch_attn_video(cudaStream_t st, const AttnArgs& a, int LqPad, size
 int launch_attention(cudaStream_t st, const AttnArgs& a) {
   if (a.B <= 0) return FVTG_OK;
   {
-    static const bool tc = [] { const char* e = getenv("FVTG_ATTN_TC"); return !e || atoi(e) != 0; }();
-    if (tc) return launch_attention_tc(st, a);
+    // tcgen05 kernel (attn_tc.cu): always for Lk > 160; FVTG_ATTN_TC=1 forces it for the short shapes too
+    static const int tc = [] { const char* e = getenv("FVTG_ATTN_TC"); return e ? atoi(e) : -1; }();
+    if (tc > 0 || (tc < 0 && a.Lk > 160)) return launch_attention_tc(st, a);
   }
   {
     const int LqPad = round_up(a.Lq, 16);
@@ -376,19 +246,8 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
                        : launch_attn_video<20, false>(st, a, LqPad, smem_v);
     }
   }
-  const int Lkpad = round_up(a.Lk, 64);
-  const size_t smem = static_cast<size_t>(Lkpad) * ATT_KS * 2 + 32 * static_cast<size_t>(Lkpad + 8) * 2;
-  if (smem > 220 * 1024) return fail(FVTG_EINVAL, "attention: %d keys exceed shared memory", a.Lk);
-  static thread_local size_t set = 0;
-  if (smem > set) {
-    FVTG_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    set = smem;
-  }
-  ProfScope prof(st, PC_ATTN);
-  attention_kernel<<<a.B * 8, ATT_THREADS, smem, st>>>(a, Lkpad);
-  FVTG_LAUNCH_CHECK("attention_kernel");
-  return FVTG_OK;
+  // everything else (long videos: TACoS, Charades-STA VGG; odd layouts) runs on the tcgen05 kernel
+  return launch_attention_tc(st, a);
 }
 
 }  // namespace fvtg

@@ -270,6 +270,365 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Keys that fit one block (every QVHighlights / Charades-STA shape): a PERSISTENT variant of the
+// same CTA.  Work items (video, query block, head pair) are dealt round-robin to the resident CTAs;
+// Q / K / V of item i+1 stream into the second shared-memory stage while item i computes, barriers
+// and the 128 TMEM columns are set up once per CTA, and the softmax arithmetic runs on packed
+// fp32 pairs with three-input maxima in 8-key groups whose masking state (below klen / below
+// v_first) is warp-uniform, so fully valid groups carry no select instructions at all.
+
+// maximum over the first nv (of W) score columns in u[]
+template <int W>
+__device__ __forceinline__ float chunk_max(const uint32_t* u, int nv, float mx) {
+#pragma unroll
+  for (int g = 0; g < W / 8; ++g) {
+    const int lo = g * 8;
+    if (lo + 8 <= nv) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2)
+        mx = max3f(mx, __uint_as_float(u[lo + j]), __uint_as_float(u[lo + j + 1]));
+    } else if (lo < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, lo + j < nv ? __uint_as_float(u[lo + j]) : -INFINITY);
+    }
+  }
+  return mx;
+}
+
+// p = 2^(s * sc + noff) for the first nv columns (0 beyond); pk = bf16 pairs of p with the columns
+// below n0 zeroed (keys that carry no value); acc_all / acc_val = packed partial sums of p over all
+// valid keys / over the value-carrying ones
+template <int W>
+__device__ __forceinline__ void chunk_softmax(const uint32_t* u, uint32_t* pk, int nv, int n0, float sc,
+                                              float noff, uint64_t& acc_all, uint64_t& acc_val) {
+  const uint64_t sc2 = f2_pack(sc, sc), off2 = f2_pack(noff, noff);
+#pragma unroll
+  for (int g = 0; g < W / 8; ++g) {
+    const int lo = g * 8;
+    if (lo >= nv) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[g * 4 + j] = 0u;
+    } else if (lo + 8 <= nv && lo >= n0) {          // 8 valid keys, all with a value
+      uint64_t s2 = 0ull;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x, y;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(u[lo + 2 * j]), __uint_as_float(u[lo + 2 * j + 1])), sc2, off2), x, y);
+        const float e0 = ex2f(x), e1 = ex2f(y);
+        s2 = f2_add(s2, f2_pack(e0, e1));
+        pk[g * 4 + j] = pack_bf16(e0, e1);
+      }
+      acc_all = f2_add(acc_all, s2);
+      acc_val = f2_add(acc_val, s2);
+    } else if (lo + 8 <= nv && lo + 8 <= n0) {      // 8 valid keys, none with a value
+      uint64_t s2 = 0ull;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x, y;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(u[lo + 2 * j]), __uint_as_float(u[lo + 2 * j + 1])), sc2, off2), x, y);
+        s2 = f2_add(s2, f2_pack(ex2f(x), ex2f(y)));
+        pk[g * 4 + j] = 0u;
+      }
+      acc_all = f2_add(acc_all, s2);
+    } else {                                         // the group straddles klen or v_first
+      float sa = 0.f, sv = 0.f, e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = ex2f(fmaf(__uint_as_float(u[lo + j]), sc, noff));
+        t = lo + j < nv ? t : 0.f;
+        sa += t;
+        t = lo + j >= n0 ? t : 0.f;
+        sv += t;
+        e[j] = t;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[g * 4 + j] = pack_bf16(e[2 * j], e[2 * j + 1]);
+      acc_all = f2_add(acc_all, f2_pack(sa, 0.f));
+      acc_val = f2_add(acc_val, f2_pack(sv, 0.f));
+    }
+  }
+}
+
+#define ATC_TRACE(role, it, ev)                                                         \
+  do {                                                                                  \
+    if (a.trace && blockIdx.x == 0 && (it) < 8)                                         \
+      a.trace[3072 + (role) * 128 + (it) * 16 + (ev)] = clock64();                      \
+  } while (0)
+
+// RES: the whole score row (NB <= 96 keys) is fetched from TMEM in one go and stays in registers
+// for both softmax passes (one TMEM round trip per head instead of seven; 3 CTAs per SM at 128
+// registers); otherwise the row is walked in 32-column chunks (4 CTAs per SM).
+template <bool RES>
+__global__ void __launch_bounds__(ATC_THREADS, RES ? 3 : 4)
+attn_tc1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnArgs a, const int QR, const int NB,
+                const int nqb, const int kv_shared, const int nitems) {
+  extern __shared__ uint8_t atc_raw[];
+  uint8_t* smem = atc_raw + ((1024u - (smem_u32(atc_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* stage_free = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_ready = bars + 5;
+  uint64_t* o_full = bars + 6;
+  uint64_t* o_free = bars + 7;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t q_bytes = static_cast<uint32_t>(QR) * 128u, k_bytes = static_cast<uint32_t>(NB) * 128u;
+  const uint32_t stage_bytes = q_bytes + k_bytes * (kv_shared ? 1u : 2u);
+  uint8_t* stage0 = smem + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmK);
+      prefetch_tmap(&tmV);
+      mbar_init(&kv_full[0], 1);
+      mbar_init(&kv_full[1], 1);
+      mbar_init(&stage_free[0], 1);
+      mbar_init(&stage_free[1], 1);
+      mbar_init(s_full, 1);
+      mbar_init(p_ready, 4);
+      mbar_init(o_full, 1);
+      mbar_init(o_free, 4);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, 128);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tmem_o = tmem + 64;
+  const int G = static_cast<int>(gridDim.x);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t idS = umma_idesc_bf16(128, NB);
+      const uint32_t idO = umma_idesc_bf16(128, 64) | (1u << 16);   // B operand MN-major (rows = keys)
+      auto issue_loads = [&](int w, int s) {
+        const int pair = w & 3, qb = (w >> 2) % nqb, b = (w >> 2) / nqb;
+        uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
+        mbar_expect_tx(&kv_full[s], stage_bytes);
+        tma_load_2d(st, &tmQ, pair * 64, b * a.Lq + qb * 128, &kv_full[s]);
+        tma_load_2d(st + q_bytes, &tmK, pair * 64, b * a.Lk, &kv_full[s]);
+        if (!kv_shared) tma_load_2d(st + q_bytes + k_bytes, &tmV, pair * 64, b * a.Lk, &kv_full[s]);
+      };
+      if (static_cast<int>(blockIdx.x) < nitems) issue_loads(blockIdx.x, 0);
+      uint32_t n = 0;   // score tiles issued so far
+      int i = 0;
+      for (int w = blockIdx.x; w < nitems; w += G, ++i) {
+        const int s = i & 1;
+        const uint32_t st_u = smem_u32(stage0 + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t sK_u = st_u + q_bytes, sV_u = kv_shared ? sK_u : sK_u + k_bytes;
+        ATC_TRACE(0, i, 0);
+        mbar_wait(&kv_full[s], (i >> 1) & 1);
+        tc_fence_after();
+        ATC_TRACE(0, i, 1);
+        for (int h = 0; h < 2; ++h) {
+          if (n > 0) {   // O of the previous head sits in the dead score columns [64,128): read out?
+            mbar_wait(o_free, (n - 1) & 1u);
+            tc_fence_after();
+          }
+          const uint64_t dq = umma_desc_sw128(st_u) + 4 * h;   // head h = 64-byte half of the 128-byte row
+          const uint64_t dk = umma_desc_sw128(sK_u) + 4 * h;
+          umma_bf16(tmem, dq, dk, idS, 0u);
+          umma_bf16(tmem, dq + 2, dk + 2, idS, 1u);
+          umma_commit(s_full);
+          ATC_TRACE(0, i, 2 + 4 * h);
+          if (h == 0 && w + G < nitems) {   // next item's operands stream in behind this item's softmax
+            if (i >= 1) mbar_wait(&stage_free[s ^ 1], ((i - 1) >> 1) & 1);
+            issue_loads(w + G, s ^ 1);
+          }
+          ATC_TRACE(0, i, 3 + 4 * h);
+          mbar_wait(p_ready, n & 1u);
+          tc_fence_after();
+          ATC_TRACE(0, i, 4 + 4 * h);
+          const uint64_t dv = umma_desc_sw128(sV_u);
+          for (int j = 0; j < NB / 16; ++j)   // 16 keys = 8 packed TMEM columns = 2048 bytes of V rows
+            umma_bf16_ts(tmem_o, tmem + 8 * j, dv + 128 * j, idO, j ? 1u : 0u);
+          umma_commit(o_full);
+          ATC_TRACE(0, i, 5 + 4 * h);
+          ++n;
+        }
+        umma_commit(&stage_free[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+    uint32_t n = 0;
+    uint32_t u[32];
+    int klen_next = 0;
+    if (static_cast<int>(blockIdx.x) < nitems) klen_next = a.klen_src[(blockIdx.x >> 2) / nqb];
+    int it = 0;
+    const bool tr = warp == 1 && lane == 0;
+    for (int w = blockIdx.x; w < nitems; w += G, ++it) {
+      const int pair = w & 3, qb = (w >> 2) % nqb, b = (w >> 2) / nqb;
+      int klen = a.kbase + klen_next;
+      if (klen > a.Lk) klen = a.Lk;
+      if (w + G < nitems) klen_next = a.klen_src[((w + G) >> 2) / nqb];
+      const int row = qb * 128 + r;
+      const bool wactive = qb * 128 + q * 32 < a.Lq;   // warp-uniform: some row of this warp exists
+      for (int h = 0; h < 2; ++h, ++n) {
+        if (tr) ATC_TRACE(1, it, 0 + 8 * h);
+        mbar_wait(s_full, n & 1u);
+        tc_fence_after();
+        if (tr) ATC_TRACE(1, it, 1 + 8 * h);
+        float lsum = 0.f, tsum = 0.f;
+        if (wactive) {
+          float mx = -INFINITY;
+          uint64_t acc_all = 0ull, acc_val = 0ull;
+          uint32_t pk[16];
+          if constexpr (RES) {
+            uint32_t u1[32], u2[32];
+            tmem_ld32(tmem + lane_addr, u);
+            if (NB >= 64) tmem_ld32(tmem + lane_addr + 32, u1);
+            else if (NB > 32) tmem_ld16(tmem + lane_addr + 32, u1);
+            if (NB >= 96) tmem_ld32(tmem + lane_addr + 64, u2);
+            else if (NB > 64) tmem_ld16(tmem + lane_addr + 64, u2);
+            tmem_ld_wait();
+            mx = chunk_max<32>(u, klen, mx);
+            if (NB > 32) mx = chunk_max<32>(u1, klen - 32, mx);
+            if (NB > 64) mx = chunk_max<32>(u2, klen - 64, mx);
+            const float noff = -(mx == -INFINITY ? 0.f : mx) * sc;
+            if (tr) ATC_TRACE(1, it, 2 + 8 * h);
+            chunk_softmax<32>(u, pk, klen, a.v_first, sc, noff, acc_all, acc_val);
+            tmem_st16(tmem + lane_addr, pk);
+            if (NB > 32) {
+              chunk_softmax<32>(u1, pk, klen - 32, a.v_first - 32, sc, noff, acc_all, acc_val);
+              if (NB >= 64) tmem_st16(tmem + lane_addr + 16, pk);
+              else tmem_st8(tmem + lane_addr + 16, pk);
+            }
+            if (NB > 64) {
+              chunk_softmax<32>(u2, pk, klen - 64, a.v_first - 64, sc, noff, acc_all, acc_val);
+              if (NB >= 96) tmem_st16(tmem + lane_addr + 32, pk);
+              else tmem_st8(tmem + lane_addr + 32, pk);
+            }
+          } else {
+            int c0 = 0;
+            for (; c0 + 32 <= NB; c0 += 32) {
+              if (klen - c0 <= 0) break;
+              tmem_ld32(tmem + lane_addr + c0, u);
+              tmem_ld_wait();
+              mx = chunk_max<32>(u, klen - c0, mx);
+            }
+            if ((NB & 16) && klen - (NB - 16) > 0) {
+              tmem_ld16(tmem + lane_addr + NB - 16, u);
+              tmem_ld_wait();
+              mx = chunk_max<16>(u, klen - (NB - 16), mx);
+            }
+            const float noff = -(mx == -INFINITY ? 0.f : mx) * sc;
+            if (tr) ATC_TRACE(1, it, 2 + 8 * h);
+            for (c0 = 0; c0 + 32 <= NB; c0 += 32) {
+              const int nv = klen - c0;
+              if (nv > 0) {
+                tmem_ld32(tmem + lane_addr + c0, u);
+                tmem_ld_wait();
+              }
+              chunk_softmax<32>(u, pk, nv, a.v_first - c0, sc, noff, acc_all, acc_val);
+              tmem_st16(tmem + lane_addr + (c0 >> 1), pk);
+            }
+            if (NB & 16) {
+              c0 = NB - 16;
+              const int nv = klen - c0;
+              if (nv > 0) {
+                tmem_ld16(tmem + lane_addr + c0, u);
+                tmem_ld_wait();
+              }
+              chunk_softmax<16>(u, pk, nv, a.v_first - c0, sc, noff, acc_all, acc_val);
+              tmem_st8(tmem + lane_addr + (c0 >> 1), pk);
+            }
+          }
+          tmem_st_wait();
+          float x, y;
+          f2_unpack(acc_all, x, y);
+          lsum = x + y;
+          f2_unpack(acc_val, x, y);
+          tsum = x + y;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        if (tr) ATC_TRACE(1, it, 3 + 8 * h);
+
+        mbar_wait(o_full, n & 1u);
+        tc_fence_after();
+        if (tr) ATC_TRACE(1, it, 4 + 8 * h);
+        if (wactive) {
+          tmem_ld32(tmem_o + lane_addr + 32 * h, u);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+        if (wactive && row < a.Lq) {
+          const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+          const int hh = pair * 2 + h;
+          const size_t grow = static_cast<size_t>(b) * a.Lq + row;
+          uint4* dst = reinterpret_cast<uint4*>(a.out + grow * 256 + hh * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(u[8 * i + 0]) * inv, __uint_as_float(u[8 * i + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(u[8 * i + 2]) * inv, __uint_as_float(u[8 * i + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(u[8 * i + 4]) * inv, __uint_as_float(u[8 * i + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(u[8 * i + 6]) * inv, __uint_as_float(u[8 * i + 7]) * inv);
+            dst[i] = v;
+          }
+          if (a.tsum) a.tsum[static_cast<size_t>(hh) * a.B * a.Lq + grow] = tsum * inv;
+        }
+        if (tr) ATC_TRACE(1, it, 5 + 8 * h);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+template <bool RES>
+static int launch_attn_tc1(cudaStream_t st, const AttnArgs& a, int QR, int NB, int nqb, bool kv_shared) {
+  const int stage = (QR + NB * (kv_shared ? 1 : 2)) * 128;
+  // the score MMA always reads 128 A rows from the start of a stage's Q tile: keep them inside the allocation
+  const int tail = stage >= ATC_UNIT ? 0 : ATC_UNIT - stage;
+  const int smem = 1024 + 2 * stage + tail + 1024;
+  static thread_local int smem_set = 0;
+  if (smem > smem_set) {
+    FVTG_CUDA_OK(cudaFuncSetAttribute(attn_tc1_kernel<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FVTG_CUDA_OK(cudaFuncSetAttribute(attn_tc1_kernel<RES>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+    smem_set = smem;
+  }
+  // resident CTAs per SM: registers (launch bounds) / 128 TMEM columns each / shared memory (+1 KB reserved per CTA)
+  int per_sm = RES ? 3 : 4;
+  const int by_smem = (227 * 1024) / (smem + 1024);
+  if (by_smem < per_sm) per_sm = by_smem < 1 ? 1 : by_smem;
+  const int nitems = a.B * nqb * 4;
+  const int grid = nitems < per_sm * sm_count() ? nitems : per_sm * sm_count();
+  CUtensorMap tq, tk, tv;
+  FVTG_TRY(make_tmap_bf16(&tq, a.q, static_cast<uint64_t>(a.B) * a.Lq, 256, a.ldq, QR, 64));
+  FVTG_TRY(make_tmap_bf16(&tk, a.k, static_cast<uint64_t>(a.B) * a.Lk, 256, a.ldk, NB, 64));
+  FVTG_TRY(make_tmap_bf16(&tv, a.v, static_cast<uint64_t>(a.B) * a.Lk, 256, a.ldv, NB, 64));
+  ProfScope prof(st, PC_ATTN);
+  FVTG_CUDA_OK(launch_pdl(attn_tc1_kernel<RES>, dim3(grid), dim3(ATC_THREADS), smem, st, tq, tk, tv, a, QR, NB, nqb,
+                          kv_shared ? 1 : 0, nitems));
+  FVTG_LAUNCH_CHECK("attn_tc1_kernel");
+  return FVTG_OK;
+}
+
 template <bool MULTI>
 static int launch_attn_tc_t(cudaStream_t st, const AttnArgs& a, int QR, int NB, int nkb, int nqb,
                             bool kv_shared) {
@@ -290,11 +649,19 @@ static int launch_attn_tc_t(cudaStream_t st, const AttnArgs& a, int QR, int NB, 
   return FVTG_OK;
 }
 
-int launch_attention_tc(cudaStream_t st, const AttnArgs& a) {
-  if (a.B <= 0) return FVTG_OK;
+int launch_attention_tc(cudaStream_t st, const AttnArgs& a_in) {
+  if (a_in.B <= 0) return FVTG_OK;
+  AttnArgs a = a_in;
+  {  // debug: FVTG_ATTN_TRACE_T2V=1 keeps the clock64 trace of cross-attention launches only
+    static const bool t2v_only = [] { const char* e = getenv("FVTG_ATTN_TRACE_T2V"); return e && atoi(e) != 0; }();
+    if (t2v_only && !a.tsum) a.trace = nullptr;
+  }
   const int nqb = (a.Lq + 127) / 128;
   const int QR = a.Lq >= 128 ? 128 : round_up(a.Lq, 8);
   const bool kv_shared = (a.k == a.v) && (a.ldk == a.ldv);
+  static const bool persistent = [] { const char* e = getenv("FVTG_ATTN_PERSIST"); return !e || atoi(e) != 0; }();
+  if (a.Lk <= 96 && persistent) return launch_attn_tc1<true>(st, a, QR, round_up(a.Lk, 16), nqb, kv_shared);
+  if (a.Lk <= 128 && persistent) return launch_attn_tc1<false>(st, a, QR, round_up(a.Lk, 16), nqb, kv_shared);
   if (a.Lk <= 128) return launch_attn_tc_t<false>(st, a, QR, round_up(a.Lk, 16), 1, nqb, kv_shared);
   return launch_attn_tc_t<true>(st, a, QR, 128, (a.Lk + 127) / 128, nqb, kv_shared);
 }

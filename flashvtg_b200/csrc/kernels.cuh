@@ -45,9 +45,6 @@ struct LayerArgs {
 };
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args);
-// same contract on CTA pairs (cta_group::2 MMAs, weight tiles split between the two SMs of a TPC)
-int launch_layer_pair(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
-                      const LayerArgs& args);
 
 // fp32 tile-blocked rows -> row-major fp32: dst[(b * rows_out + j)][256] = src row (b * rows_in + j), j < rows_out
 int launch_unblock(cudaStream_t st, const float* src_blk, float* dst, int B, int rows_in, int rows_out);

@@ -43,7 +43,7 @@ constexpr int LK_OFF_W = 4 * LK_UNIT;        // weight ring
 constexpr int LK_OFF_BAR = LK_OFF_W + LK_STAGES * LK_STAGE;
 constexpr int LK_OFF_STAT = LK_OFF_BAR + 256;
 constexpr int LK_OFF_PAR = LK_OFF_STAT + 2 * 4 * 128 * 8;   // [2 phases][4 quarters][128 rows] float2
-constexpr int LK_PAR_FLOATS = 256 * 3 + 1024 + 256 * 3;
+constexpr int LK_PAR_FLOATS = 256 * 3 + 1024 + 256 * 4;
 constexpr int LK_SMEM_BYTES = LK_OFF_PAR + LK_PAR_FLOATS * 4 + 1024 /*align slack*/;
 static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 KB limit");
 
@@ -57,6 +57,22 @@ static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// two packed fp32 pairs (16 bytes) from shared / global memory
+__device__ __forceinline__ ulonglong2 ld_p4(const float* p) { return *reinterpret_cast<const ulonglong2*>(p); }
+__device__ __forceinline__ uint64_t pk2(const uint32_t* u, int j) {
+  return f2_pack(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
+}
+__device__ __forceinline__ void unpk2(uint64_t v, uint32_t* u, int j) {
+  float x, y;
+  f2_unpack(v, x, y);
+  u[2 * j] = __float_as_uint(x);
+  u[2 * j + 1] = __float_as_uint(y);
+}
+__device__ __forceinline__ uint32_t bf16x2_of(uint64_t v) {
+  float x, y;
+  f2_unpack(v, x, y);
+  return pack_bf16(x, y);
+}
 
 __global__ void __launch_bounds__(LK_THREADS, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWo,
@@ -88,6 +104,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   float* s_b2 = s_par + 1792;
   float* s_g2 = s_par + 2048;
   float* s_be2 = s_par + 2304;
+  float* s_be1z = s_par + 2560;   // be1 + b2: the SA-mode FFN residual LN1(z) enters Z with ff2's bias folded in
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +144,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     s_b2[i] = g.b2[i];
     s_g2[i] = g.g2[i];
     s_be2[i] = g.be2[i];
+    s_be1z[i] = g.be1[i] + g.b2[i];
   }
   for (int i = threadIdx.x; i < 1024; i += LK_THREADS) s_b1[i] = g.b1[i];
   pdl_wait();   // everything above touched only constants / on-chip state
@@ -262,6 +280,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(ln_ready, it & 1);
         tc_fence_after();
         LK_TRACE(0, 4);
+        // the fp32 residual block of this CTA's next tile (128 KB, contiguous in the tile-blocked layout) was
+        // written a whole layer ago: pull it back into L2 now, a full FFN ahead of the epilogue that reads it
+        if (g.tile_rows == 128 && tile + static_cast<int>(gridDim.x) < ntiles && !(g.dbg & 8)) {
+          const float* nxt = g.yf + static_cast<size_t>(tile + gridDim.x) * (128 * 256);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bulk_prefetch_l2(nxt + i * 4096, 16384);
+        }
         ff1(0);
         ff1(1);
         LK_TRACE(0, 5);
@@ -294,49 +319,54 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool tr = (warp == 4 && lane == 0);
 
       // ---- epilogue 1: z = H + bo + x ; LayerNorm1 -> sA ; FFN residual into Z -----------------
+      // (packed fp32 pairs throughout: add.f32x2 / fma.rn.f32x2 halve the FP instruction count)
       if (tr) LK_TRACE(1, 0);
-      float4 rr[8];
+      ulonglong2 rr[8];
+      const float* ysrc = yblk + static_cast<size_t>(qt) * (16 * 512);   // this thread's column quarter
       {  // the first residual chunk does not depend on the MMA: fetch it before waiting
-        const int c0 = qt * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          rr[i] = ldres ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) rr[i] = ldres ? ld_p4(ysrc + i * 512) : make_ulonglong2(0ull, 0ull);
       }
       mbar_wait(z1_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 1);
-      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      float shift = 0.f;
+      uint64_t nsh2 = 0ull, a1 = 0ull, a2 = 0ull;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = qt * 64 + c * 32;
         tmem_ld32(tmem_h + lane_addr + c0, u);
-        if (c == 1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            rr[i] = ldres ? ld_f4(yblk + ((c0 >> 2) + i) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = ld_f4(s_bo + c0 + 4 * i);
-          u[4 * i + 0] = __float_as_uint(__uint_as_float(u[4 * i + 0]) + b.x + rr[i].x);
-          u[4 * i + 1] = __float_as_uint(__uint_as_float(u[4 * i + 1]) + b.y + rr[i].y);
-          u[4 * i + 2] = __float_as_uint(__uint_as_float(u[4 * i + 2]) + b.z + rr[i].z);
-          u[4 * i + 3] = __float_as_uint(__uint_as_float(u[4 * i + 3]) + b.w + rr[i].w);
+          const ulonglong2 b = ld_p4(s_bo + c0 + 4 * i);
+          unpk2(f2_add(f2_add(pk2(u, 2 * i), b.x), rr[i].x), u, 2 * i);
+          unpk2(f2_add(f2_add(pk2(u, 2 * i + 1), b.y), rr[i].y), u, 2 * i + 1);
         }
-        if (c == 0) shift = __uint_as_float(u[0]);
+        if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(u[j]) - shift;
-          s1 += d;
-          s2 += d * d;
+          for (int i = 0; i < 8; ++i) rr[i] = ldres ? ld_p4(ysrc + (8 + i) * 512) : make_ulonglong2(0ull, 0ull);
+          shift = __uint_as_float(u[0]);
+          nsh2 = f2_pack(-shift, -shift);
         }
         tmem_st32(tmem + lane_addr + c0, u);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint64_t d = f2_add(pk2(u, j), nsh2);
+          a1 = f2_add(a1, d);
+          a2 = f2_fma(d, d, a2);
+        }
+      }
+      {
+        float s1a, s1b, s2a, s2b;
+        f2_unpack(a1, s1a, s1b);
+        f2_unpack(a2, s2a, s2b);
+        const float s1 = s1a + s1b, s2 = s2a + s2b;
+        // per-quarter partial: (mean of 64, centred sum of squares of 64)
+        s_stat[qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
       }
       tmem_st_wait();
       if (tr) LK_TRACE(1, 2);
-      // per-quarter partial: (mean of 64, centred sum of squares of 64)
-      s_stat[qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
       epi_bar_sync();
       float mean, rstd;
       {
@@ -346,28 +376,40 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float m2 = a0.y + a1.y + a2.y + a3.y + 64.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
         rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
       }
+      {
+        const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = qt * 64 + c * 32;
-        tmem_ld32(tmem + lane_addr + c0, u);
-        tmem_ld_wait();
-        float v[32];
+        for (int c = 0; c < 2; ++c) {
+          const int c0 = qt * 64 + c * 32;
+          tmem_ld32(tmem + lane_addr + c0, u);
+          tmem_ld_wait();
+          uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 gm = ld_f4(s_g1 + c0 + 4 * i), bt = ld_f4(s_be1 + c0 + 4 * i);
-          v[4 * i + 0] = (__uint_as_float(u[4 * i + 0]) - mean) * rstd * gm.x + bt.x;
-          v[4 * i + 1] = (__uint_as_float(u[4 * i + 1]) - mean) * rstd * gm.y + bt.y;
-          v[4 * i + 2] = (__uint_as_float(u[4 * i + 2]) - mean) * rstd * gm.z + bt.z;
-          v[4 * i + 3] = (__uint_as_float(u[4 * i + 3]) - mean) * rstd * gm.w + bt.w;
-        }
-        st_shared_bf16x32(sA + (c0 >> 6) * LK_UNIT, r, (c0 & 63) >> 3, v);
-        if (g.mode == LAYER_SA) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(v[j]);
+          for (int i = 0; i < 8; ++i) {
+            const ulonglong2 gm = ld_p4(s_g1 + c0 + 4 * i), bt = ld_p4(s_be1 + c0 + 4 * i);
+            const uint64_t t0 = f2_fma(pk2(u, 2 * i), rs2, nm2), t1 = f2_fma(pk2(u, 2 * i + 1), rs2, nm2);
+            w[2 * i] = bf16x2_of(f2_fma(t0, gm.x, bt.x));
+            w[2 * i + 1] = bf16x2_of(f2_fma(t1, gm.y, bt.y));
+            if (g.mode == LAYER_SA) {   // the FFN residual is LN1(z): Z <- LN1(z) + b2
+              const ulonglong2 bz = ld_p4(s_be1z + c0 + 4 * i);
+              unpk2(f2_fma(t0, gm.x, bz.x), u, 2 * i);
+              unpk2(f2_fma(t1, gm.y, bz.y), u, 2 * i + 1);
+            } else {                    // ... the pre-LN1 sum: Z <- z + b2
+              const ulonglong2 bz = ld_p4(s_b2 + c0 + 4 * i);
+              unpk2(f2_add(pk2(u, 2 * i), bz.x), u, 2 * i);
+              unpk2(f2_add(pk2(u, 2 * i + 1), bz.y), u, 2 * i + 1);
+            }
+          }
           tmem_st32(tmem + lane_addr + c0, u);
+          uint8_t* unit = sA + (c0 >> 6) * LK_UNIT;
+          const int cf = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(unit + sw128_off(r, cf + q4)) =
+                make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
         }
       }
-      if (g.mode == LAYER_SA) tmem_st_wait();
+      tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -409,33 +451,40 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (tr) LK_TRACE(1, 5 + 2 * p);
       }
 
-      // ---- final epilogue: y = LayerNorm2(Z + b2) -> residual stream / bf16 operands --------
+      // ---- final epilogue: y = LayerNorm2(Z) (b2 is already in Z) -> residual stream / bf16 operands --
       int prow = row;
       if (g.pos_mod > 0) prow = row % g.pos_mod;
       const bool st_pos = g.out_pb && inb && (g.pos_rowlim <= 0 || prow < g.pos_rowlim);
       const bool ld_pos = st_pos && g.pos && !(g.dbg & 2);
+      const bool st_ok = inb && !(g.dbg & 4);
+      const bool st_pb = st_pos && !(g.dbg & 4);
       mbar_wait(z2_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 20);
-      shift = 0.f; s1 = 0.f; s2 = 0.f;
+      a1 = 0ull;
+      a2 = 0ull;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int c0 = qt * 64 + c * 32;
-        tmem_ld32(tmem + lane_addr + c0, u);
+        tmem_ld32(tmem + lane_addr + qt * 64 + c * 32, u);
         tmem_ld_wait();
-        if (c == 0) shift = __uint_as_float(u[0]) + s_b2[c0];
+        if (c == 0) {
+          shift = __uint_as_float(u[0]);
+          nsh2 = f2_pack(-shift, -shift);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = ld_f4(s_b2 + c0 + 4 * i);
-          const float d0 = __uint_as_float(u[4 * i + 0]) + b.x - shift;
-          const float d1 = __uint_as_float(u[4 * i + 1]) + b.y - shift;
-          const float d2 = __uint_as_float(u[4 * i + 2]) + b.z - shift;
-          const float d3 = __uint_as_float(u[4 * i + 3]) + b.w - shift;
-          s1 += (d0 + d1) + (d2 + d3);
-          s2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        for (int j = 0; j < 16; ++j) {
+          const uint64_t d = f2_add(pk2(u, j), nsh2);
+          a1 = f2_add(a1, d);
+          a2 = f2_fma(d, d, a2);
         }
       }
-      s_stat[512 + qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
+      {
+        float s1a, s1b, s2a, s2b;
+        f2_unpack(a1, s1a, s1b);
+        f2_unpack(a2, s2a, s2b);
+        const float s1 = s1a + s1b, s2 = s2a + s2b;
+        s_stat[512 + qt * 128 + r] = make_float2(shift + s1 * (1.f / 64.f), s2 - s1 * s1 * (1.f / 64.f));
+      }
       epi_bar_sync();
       if (tr) LK_TRACE(1, 21);
       {
@@ -445,58 +494,45 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float m2 = a0.y + a1.y + a2.y + a3.y + 64.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
         rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
       }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = qt * 64 + c * 32;
-        tmem_ld32(tmem + lane_addr + c0, u);
+      {
+        const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
+        float* ydst = yblk + static_cast<size_t>(qt) * (16 * 512);
+        const float* psrc = nullptr;   // this lane's position row, first column of its quarter
+        size_t pstep = 0;              // floats between consecutive 4-column groups
         if (ld_pos) {
-          if (g.pos_mod > 0) {
-            const float* ps = g.pos + static_cast<size_t>(prow) * 256 + c0;
+          if (g.pos_mod > 0) { psrc = g.pos + static_cast<size_t>(prow) * 256 + qt * 64; pstep = 4; }
+          else if (g.pos_cmp_L > 0) {
+            psrc = g.pos + (static_cast<size_t>(qt * 16) * g.pos_cmp_L + row % g.pos_cmp_L) * 4;
+            pstep = static_cast<size_t>(g.pos_cmp_L) * 4;
+          } else { psrc = g.pos + blk + static_cast<size_t>(qt) * (16 * 512); pstep = 512; }
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + 4 * i);
-          } else if (g.pos_cmp_L > 0) {
-            const float* ps = g.pos + (static_cast<size_t>(c0 >> 2) * g.pos_cmp_L + row % g.pos_cmp_L) * 4;
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tmem + lane_addr + qt * 64 + c * 32, u);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + static_cast<size_t>(i) * g.pos_cmp_L * 4);
-          } else {
-            const float* ps = g.pos + blk;
+          for (int h16 = 0; h16 < 2; ++h16) {   // 16 columns: one 32-byte sector of each bf16 output row
+            const int c0 = qt * 64 + c * 32 + h16 * 16;
+            uint32_t w[8], wp[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = ld_f4(ps + ((c0 >> 2) + i) * 512);
+            for (int i = 0; i < 4; ++i) {
+              const int g4 = c * 8 + h16 * 4 + i;   // 4-column group within the quarter
+              const ulonglong2 gm = ld_p4(s_g2 + c0 + 4 * i), bt = ld_p4(s_be2 + c0 + 4 * i);
+              ulonglong2 y;
+              y.x = f2_fma(f2_fma(pk2(u, h16 * 8 + 2 * i), rs2, nm2), gm.x, bt.x);
+              y.y = f2_fma(f2_fma(pk2(u, h16 * 8 + 2 * i + 1), rs2, nm2), gm.y, bt.y);
+              if (st_ok) *reinterpret_cast<ulonglong2*>(ydst + g4 * 512) = y;
+              w[2 * i] = bf16x2_of(y.x);
+              w[2 * i + 1] = bf16x2_of(y.y);
+              if (g.out_pb) {
+                const ulonglong2 pv = psrc ? ld_p4(psrc + g4 * pstep) : make_ulonglong2(0ull, 0ull);
+                wp[2 * i] = bf16x2_of(f2_add(y.x, pv.x));
+                wp[2 * i + 1] = bf16x2_of(f2_add(y.y, pv.y));
+              }
+            }
+            if (g.out_b && st_ok) st_global_v8(g.out_b + static_cast<size_t>(row) * 256 + c0, w);
+            if (g.out_pb && st_pb) st_global_v8(g.out_pb + static_cast<size_t>(row) * 256 + c0, wp);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = ld_f4(s_b2 + c0 + 4 * i), gm = ld_f4(s_g2 + c0 + 4 * i),
-                       bt = ld_f4(s_be2 + c0 + 4 * i);
-          v[4 * i + 0] = (__uint_as_float(u[4 * i + 0]) + b.x - mean) * rstd * gm.x + bt.x;
-          v[4 * i + 1] = (__uint_as_float(u[4 * i + 1]) + b.y - mean) * rstd * gm.y + bt.y;
-          v[4 * i + 2] = (__uint_as_float(u[4 * i + 2]) + b.z - mean) * rstd * gm.z + bt.z;
-          v[4 * i + 3] = (__uint_as_float(u[4 * i + 3]) + b.w - mean) * rstd * gm.w + bt.w;
-        }
-        const bool st_ok = inb && !(g.dbg & 4);
-        if (st_ok) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(yblk + ((c0 >> 2) + i) * 512) =
-                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (g.out_b)
-          st_global_bf16x32_paired(g.out_b + static_cast<size_t>(row) * 256 + c0, 256, st_ok, v);
-        if (g.out_pb) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[4 * i + 0] += rr[i].x;
-            v[4 * i + 1] += rr[i].y;
-            v[4 * i + 2] += rr[i].z;
-            v[4 * i + 3] += rr[i].w;
-          }
-          st_global_bf16x32_paired(g.out_pb + static_cast<size_t>(row) * 256 + c0, 256,
-                                   st_pos && !(g.dbg & 4), v);
         }
       }
       // Z is rewritten next by this same thread (epilogue 1 of the next tile), H by MMAs that
@@ -517,10 +553,6 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args) {
   if (args.M <= 0) return FVTG_OK;
-  {  // the CTA-pair (cta_group::2) variant is kept for A/B measurements
-    static const bool pair = [] { const char* e = getenv("FVTG_LAYER_PAIR"); return e && atoi(e) != 0; }();
-    if (pair) return launch_layer_pair(st, att, wo, w1, w2, args);
-  }
   static thread_local bool attr_set = false;
   if (!attr_set) {
     FVTG_CUDA_OK(cudaFuncSetAttribute(layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -433,9 +433,10 @@ def test_forward_matches_oracle_at_baseline_shapes(preset, B, Lv, Lt, ragged):
         assert np.all(np.diff(sc) <= 0)
 
 
-def test_cta_pair_layer_kernel_matches_default():
-    """The cta_group::2 variant of the fused layer kernel (FVTG_LAYER_PAIR=1, kept for A/B
-    measurements) computes the same forward as the default single-CTA kernel."""
+def test_tcgen05_attention_forced_for_short_shapes_matches_default():
+    """FVTG_ATTN_TC=1 routes the short QVHighlights shapes through the tcgen05 attention kernel too
+    (persistent, TMEM-resident softmax; by default it only serves sequences of more than 160 keys): same
+    forward as the default mma.sync kernel within the bf16 noise floor of the path."""
     import subprocess
     import sys
     code = r'''
@@ -454,14 +455,14 @@ torch.save({"sal": r.saliency.cpu(), "cls": r.cls_logit.cpu(), "coord": r.coord.
 ''' % ROOT
     import tempfile
     outs = []
-    for pair in ("0", "1"):
+    for tc in ("-1", "1"):
         with tempfile.NamedTemporaryFile(suffix=".pt") as f:
-            env = dict(os.environ, FVTG_LAYER_PAIR=pair)
+            env = dict(os.environ, FVTG_ATTN_TC=tc)
             subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
             outs.append(torch.load(f.name))
     for k in outs[0]:
         e = max_rel(outs[1][k].numpy(), outs[0][k].numpy())
-        assert e < 2e-3, f"{k}: pair vs default max-norm rel err {e:.3e}"
+        assert e < TOL, f"{k}: tcgen05 attention vs default max-norm rel err {e:.3e}"
 
 
 def test_uniform_length_hint_changes_nothing():
