@@ -44,6 +44,8 @@ class FvtgResult:
     count: torch.Tensor           # (B,) int32 valid rows of boundary / windows
     nms_count: Optional[torch.Tensor]     # (B,) int32
     launches: int                 # kernels + async copies enqueued by this call
+    packed: Optional[torch.Tensor] = None   # flat fp32 buffer that nms_windows | saliency | count | nms_count are views
+                                            # of (FlashVTGB200.alloc_outputs): ONE collective gathers a shard's records
 
 
 class FlashVTGB200(torch.nn.Module):
@@ -109,12 +111,56 @@ class FlashVTGB200(torch.nn.Module):
         return p
 
     # ------------------------------------------------------------------------------- batched API
+    def packed_layout(self, B: int, Lv: int):
+        """Element offsets of the ranked-span record fields inside the flat fp32 `packed` buffer:
+        {name: (offset, numel)} and the total length.  count / nms_count are int32 views of their slots."""
+        k = self.cfg.max_num_moment
+        off, lay = 0, {}
+        for name, n in (("nms_windows", B * k * 3), ("saliency", B * Lv), ("count", B), ("nms_count", B)):
+            lay[name] = (off, n)
+            off += (n + 3) // 4 * 4   # 16-byte aligned fields
+        return lay, off
+
+    def alloc_outputs(self, B: int, Lv: int, device, nms: Optional[str] = "normal", want_heads: bool = False,
+                      want_emb: bool = False, want_dummy: bool = False) -> FvtgResult:
+        """Output tensors of one infer() call, allocated once and reusable through infer(out=...): no
+        allocation inside a serving loop.  The fields a data-parallel job gathers (nms_windows, saliency,
+        count, nms_count) are views of ONE contiguous buffer (`packed`), so a rank's records leave in a
+        single all_gather_into_tensor (flashvtg_b200.distributed.gather_packed)."""
+        cfg = self.cfg
+        dev = torch.device(device)
+        n_max, topk = cfg.num_points(Lv), cfg.max_num_moment
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        lay, total = self.packed_layout(B, Lv)
+        packed = torch.zeros(total, **f32)
+
+        def view(name, *shape, as_int=False):
+            o, n = lay[name]
+            t = packed[o:o + n]
+            return (t.view(torch.int32) if as_int else t).view(*shape)
+        do_nms = _NMS_MODES[nms] != _lib.NMS_NONE
+        return FvtgResult(
+            saliency=view("saliency", B, Lv), t2vattn=torch.empty(B, Lv, **f32),
+            dummy_tokens=torch.empty(B, cfg.num_dummies, 256, **f32) if want_dummy else None,
+            video_emb=torch.empty(B, Lv, 256, **f32) if want_emb else None,
+            cls_logit=torch.empty(B, n_max, **f32) if want_heads else None,
+            conf_logit=torch.empty(B, n_max, **f32) if want_heads else None,
+            coord=torch.empty(B, n_max, 2, **f32) if want_heads else None,
+            boundary=torch.empty(B, topk, 3, **f32), windows=torch.empty(B, topk, 3, **f32),
+            nms_windows=view("nms_windows", B, topk, 3) if do_nms else None,
+            nms_order=torch.empty(B, topk, **i32) if do_nms else None,
+            count=view("count", B, as_int=True),
+            nms_count=view("nms_count", B, as_int=True) if do_nms else None,
+            launches=0, packed=packed)
+
     @torch.no_grad()
     def infer(self, src_vid: torch.Tensor, vid_len: torch.Tensor, src_txt: torch.Tensor,
               txt_len: torch.Tensor, duration: Optional[torch.Tensor] = None,
               nms: Optional[str] = "normal", nms_thd: Optional[float] = None,
               want_heads: bool = False, want_emb: bool = False,
-              want_dummy: bool = False, uniform_len: bool = False) -> FvtgResult:
+              want_dummy: bool = False, uniform_len: bool = False,
+              out: Optional[FvtgResult] = None) -> FvtgResult:
         """Whole hot path for B videos on the current CUDA stream (no host sync).
 
         uniform_len=True is the caller's promise that every video has the same true length
@@ -139,30 +185,28 @@ class FlashVTGB200(torch.nn.Module):
             raise ValueError(f"bad input shapes {tuple(src_vid.shape)} / {tuple(src_txt.shape)} for "
                              f"v_feat_dim {cfg.v_feat_dim}, t_feat_dim {cfg.t_feat_dim}")
         # generator.py:60: the reference asserts each level fits the anchor buffer
-        assert Lv <= cfg.buffer_size, "anchor buffer overflow"
+        if Lv > cfg.buffer_size:
+            raise ValueError(f"Lv {Lv} exceeds the anchor buffer ({cfg.buffer_size} points, generator.py:60)")
         if duration is None:
             duration = vid_len.to(torch.float32) * cfg.clip_length
         duration = duration.to(device=dev, dtype=torch.float32).contiguous()
         W = self._weights(dev)
         with torch.cuda.device(dev):
             n_max = cfg.num_points(Lv)
-            topk = cfg.max_num_moment
-            f32 = dict(dtype=torch.float32, device=dev)
-            i32 = dict(dtype=torch.int32, device=dev)
-            sal = torch.empty(B, Lv, **f32)
-            t2v = torch.empty(B, Lv, **f32)
-            dummy = torch.empty(B, cfg.num_dummies, 256, **f32) if want_dummy else None
-            emb = torch.empty(B, Lv, 256, **f32) if want_emb else None
-            cls = torch.empty(B, n_max, **f32) if want_heads else None
-            conf = torch.empty(B, n_max, **f32) if want_heads else None
-            coord = torch.empty(B, n_max, 2, **f32) if want_heads else None
-            boundary = torch.empty(B, topk, 3, **f32)
-            windows = torch.empty(B, topk, 3, **f32)
-            count = torch.empty(B, **i32)
             do_nms = _NMS_MODES[nms] != _lib.NMS_NONE
-            nms_w = torch.empty(B, topk, 3, **f32) if do_nms else None
-            nms_o = torch.empty(B, topk, **i32) if do_nms else None
-            nms_c = torch.empty(B, **i32) if do_nms else None
+            if out is None:
+                out = self.alloc_outputs(B, Lv, dev, nms, want_heads, want_emb, want_dummy)
+            elif (out.saliency.shape != (B, Lv) or out.saliency.device != dev or (do_nms and out.nms_windows is None)
+                  or (want_heads and out.cls_logit is None) or (want_emb and out.video_emb is None)
+                  or (want_dummy and out.dummy_tokens is None)):
+                raise ValueError("infer(out=...): buffers were allocated for another shape / option set "
+                                 "(use alloc_outputs with the same B, Lv and flags)")
+            sal, t2v, dummy, emb = out.saliency, out.t2vattn, out.dummy_tokens, out.video_emb
+            cls, conf, coord = out.cls_logit, out.conf_logit, out.coord
+            boundary, windows, count = out.boundary, out.windows, out.count
+            nms_w = out.nms_windows if do_nms else None
+            nms_o = out.nms_order if do_nms else None
+            nms_c = out.nms_count if do_nms else None
 
             batch = _lib.FvtgBatch(B, Lv, Lt, int(bool(uniform_len) or B == 1), src_vid.data_ptr(), src_txt.data_ptr(),
                                    vid_len.data_ptr(), txt_len.data_ptr())
@@ -180,9 +224,11 @@ class FlashVTGB200(torch.nn.Module):
                                   duration.data_ptr(), C.byref(dp), C.byref(fout), C.byref(hout),
                                   C.byref(dout), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
             _lib.check(rc, "fvtg_forward")
-            launches = int(lib.fvtg_last_launch_count())
-        return FvtgResult(sal, t2v, dummy, emb, cls, conf, coord, boundary, windows, nms_w, nms_o,
-                          count, nms_c, launches)
+            out.launches = int(lib.fvtg_last_launch_count())
+        if not do_nms and out.nms_windows is not None:   # buffers reused for a call without NMS
+            return FvtgResult(sal, t2v, dummy, emb, cls, conf, coord, boundary, windows, None, None, count,
+                              None, out.launches, out.packed)
+        return out
 
     @torch.no_grad()
     def infer_host(self, src_vid: torch.Tensor, vid_len: torch.Tensor, src_txt: torch.Tensor,

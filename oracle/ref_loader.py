@@ -1,9 +1,12 @@
-"""TEST INFRASTRUCTURE ONLY - imports the UNMODIFIED reference from /root/reference.
+"""TEST INFRASTRUCTURE ONLY - imports the UNMODIFIED reference.
 
-Works only in the build container (the GPU box has no /root/reference); used by
-tests/golden/make_golden.py to generate the committed fixtures and by the CPU tests that
-cross-check oracle/forward.py against the real thing when the tree is present.  Nothing in the
-product (flashvtg_b200/) imports this module.
+The reference tree is looked up at $FLASHVTG_REFERENCE, /root/reference (the build container) and then
+baseline/_ref/ - the git-ignored copy __graft_entry__.build() installs next to the repo so that it travels
+to the GPU box for `bench.py --impl reference` (the reference is pure Python with no setup.py, so "install"
+is a file copy of its packages; oracle/shim supplies the two imports that cannot be installed offline).
+Used by tests/golden/make_golden.py to generate the committed fixtures, by the CPU tests that cross-check
+oracle/forward.py against the real thing when the tree is present, and by bench.py's reference arm.
+Nothing in the product (flashvtg_b200/) imports this module.
 """
 from __future__ import annotations
 
@@ -13,8 +16,36 @@ import types
 from argparse import Namespace
 from pathlib import Path
 
-REF_ROOT = Path(os.environ.get("FLASHVTG_REFERENCE", "/root/reference"))
 SHIM = Path(__file__).resolve().parent / "shim"
+INSTALLED = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
+REF_PACKAGES = ("FlashVTG", "blocks", "utils", "standalone_eval")
+
+
+def _find_root() -> Path:
+    env = os.environ.get("FLASHVTG_REFERENCE")
+    for cand in ([Path(env)] if env else []) + [Path("/root/reference"), INSTALLED]:
+        if (cand / "FlashVTG" / "model.py").exists():
+            return cand
+    return Path("/root/reference")
+
+
+REF_ROOT = _find_root()
+
+
+def install(src: Path = Path("/root/reference"), dst: Path = INSTALLED) -> bool:
+    """Copy the reference's Python packages (unmodified) into baseline/_ref/ - the counterpart of
+    `pip install --target baseline/_ref` for a tree without a build system.  Returns False when `src` is absent."""
+    import shutil
+    if not (src / "FlashVTG" / "model.py").exists():
+        return False
+    for pkg in REF_PACKAGES:
+        if (src / pkg).is_dir():
+            shutil.copytree(src / pkg, dst / pkg, dirs_exist_ok=True,
+                            ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "*.jsonl", "*.json", "*.md"))
+    for name in ("LISCENSE", "LICENSE"):
+        if (src / name).exists():
+            shutil.copy2(src / name, dst / name)
+    return True
 
 
 def available() -> bool:
@@ -107,3 +138,34 @@ def reference_postprocessor():
     ns = dict(torch=torch, tqdm=tqdm)
     exec(compile(src[start:], str(REF_ROOT / "FlashVTG" / "postprocessing.py"), "exec"), ns)  # noqa: S102
     return ns["PostProcessorDETR"]
+
+
+def reference_eval_functions():
+    """The reference's own eval loop pieces, imported unmodified: (compute_mr_results, post_processing_mr_nms)
+    from FlashVTG/inference.py:232,36."""
+    _ensure_path()
+    import importlib
+    inf = importlib.import_module("FlashVTG.inference")
+    return inf.compute_mr_results, inf.post_processing_mr_nms
+
+
+def reference_eval_opt(cfg) -> Namespace:
+    """The option fields compute_mr_results / eval_epoch_post_processing read (inference.py:246-352,79-87)."""
+    return Namespace(device="cpu", pin_memory=False, clip_length=cfg.clip_length, span_loss_type="l1",
+                     dset_name=cfg.dset_name, v_feat_dim=cfg.v_feat_dim, nms_thd=cfg.nms_thd,
+                     max_before_nms=50, max_after_nms=10, nms_type=cfg.nms_type)
+
+
+def bs1_loader(batch, n):
+    """What DataLoader(StartEndDataset, collate_fn=start_end_collate, batch_size=1) yields for n synthetic videos:
+    (query_meta, batched_model_inputs) with (tensor, mask) pairs cut to the true lengths (start_end_collate pads
+    to the batch maximum, which at bs=1 is the video's own length)."""
+    out = []
+    for b in range(n):
+        lv, lt = int(batch["vid_len"][b]), int(batch["txt_len"][b])
+        meta = [dict(qid=b, query="synthetic", vid=f"v{b}", duration=float(batch["duration"][b]))]
+        inputs = dict(query_feat=(batch["src_txt"][b:b + 1, :lt], batch["src_txt_mask"][b:b + 1, :lt]),
+                      video_feat=(batch["src_vid"][b:b + 1, :lv], batch["src_vid_mask"][b:b + 1, :lv]),
+                      vid=[f"v{b}"], qid=[b])
+        out.append((meta, inputs))
+    return out

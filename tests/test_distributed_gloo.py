@@ -16,6 +16,93 @@ def _free_port():
         return s.getsockname()[1]
 
 
+class _StubModel:
+    """packed_layout / cfg of FlashVTGB200 without the CUDA library (host logic only)."""
+    class cfg:  # noqa: N801
+        max_num_moment = 50
+
+    def packed_layout(self, B, Lv):
+        from flashvtg_b200.model import FlashVTGB200
+        return FlashVTGB200.packed_layout(self, B, Lv)
+
+
+def _worker_plan(rank, world, port, n_total, mode, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flashvtg_b200.distributed import PackedGather, gather_records, shard_batch, shard_plan
+        g = torch.Generator().manual_seed(7)
+        vlen = torch.randint(3, 76, (n_total,), generator=g, dtype=torch.int32)
+        vlen[0] = 75
+        full = {"vid_len": vlen, "txt_len": torch.randint(1, 33, (n_total,), generator=g, dtype=torch.int32),
+                "src_vid": torch.randn(n_total, 75, 6, generator=g), "src_txt": torch.randn(n_total, 32, 5, generator=g)}
+        plan = shard_plan(vlen, world, mode)
+        local = shard_batch(full, rank, world, mode)
+        ok = local["vid_len"].shape[0] == plan[rank].numel()
+        if plan[rank].numel() and mode != "contiguous":
+            ok = ok and local["src_vid"].shape[1] == int(local["vid_len"].max())   # cropped to the shard's longest
+        # a per-video function of the shard rows (what the kernels compute), gathered back to input order
+        res = {"score": local["vid_len"].float() * 2 + 1, "tag": local["txt_len"].to(torch.int32) + 5}
+        got = gather_records(res, n_total, plan=plan)
+        ok = ok and torch.equal(got["score"], vlen.float() * 2 + 1) and torch.equal(got["tag"], full["txt_len"] + 5)
+        # packed fast path: equal shards, one collective, views [world][B_local][...]
+        m = _StubModel()
+        B, Lv = 4, 9
+        lay, n = m.packed_layout(B, Lv)
+        packed = torch.zeros(n)
+        o, cnt = lay["saliency"]
+        packed[o:o + cnt] = torch.arange(cnt, dtype=torch.float32) + 100 * rank
+        o, cnt = lay["count"]
+        packed[o:o + cnt].view(torch.int32).copy_(torch.arange(cnt, dtype=torch.int32) + 7 * rank)
+        pg = PackedGather(m, B, Lv, "cpu")
+        slot = pg.gather(packed)
+        pg.wait(slot)
+        v = pg.views(slot)
+        for r in range(world):
+            ok = ok and torch.equal(v["saliency"][r].reshape(-1), torch.arange(B * Lv, dtype=torch.float32) + 100 * r)
+            ok = ok and torch.equal(v["count"][r], torch.arange(B, dtype=torch.int32) + 7 * r)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["contiguous", "balanced", "bucketed"])
+def test_shard_plans_and_single_collective_gather_world2(mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_plan, args=(r, 2, port, 11, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_shard_plan_properties():
+    from flashvtg_b200.distributed import shard_plan
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 5, 64, 1000):
+        ln = torch.randint(1, 200, (n,), generator=g)
+        for world in (1, 2, 8):
+            for mode in ("contiguous", "balanced", "bucketed"):
+                plan = shard_plan(ln, world, mode)
+                assert len(plan) == world
+                assert torch.equal(torch.cat(plan).sort().values, torch.arange(n))   # a partition
+            bal = shard_plan(ln, world, "balanced")
+            sizes = [int(p.numel()) for p in bal]
+            assert max(sizes) - min(sizes) <= 1
+            if n >= 8 * world:
+                clips = [int(ln[p].sum()) for p in bal]
+                assert max(clips) - min(clips) <= int(ln.max())        # within one video of each other
+                cost = [int(p.numel()) * int(ln[p].max()) for p in shard_plan(ln, world, "bucketed") if p.numel()]
+                naive = -(-n // world) * int(ln.max())
+                assert max(cost) <= naive                                  # never worse than padding to the global max
+
+
 def _worker(rank, world, port, n_total, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
