@@ -75,6 +75,10 @@ class FvtgWeights(C.Structure):
                 ("coef", f32 * MAX_LEVELS), ("x", f32), ("_pad", i32)]
 
 
+class FvtgParam(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", vp), ("numel", C.c_int64)]
+
+
 class FvtgBatch(C.Structure):
     _fields_ = [("B", i32), ("Lv", i32), ("Lt", i32), ("uniform_vid_len", i32),
                 ("vid", vp), ("txt", vp), ("vid_len", vp), ("txt_len", vp)]
@@ -122,6 +126,11 @@ class FvtgEvalBatch(C.Structure):
 SIGNATURES = {
     "fvtg_workspace_bytes": (C.c_size_t, [C.POINTER(FvtgCfg), i32, i32, i32]),
     "fvtg_chunk_videos": (i32, [C.POINTER(FvtgCfg), i32, i32]),
+    "fvtg_packed_weights_bytes": (C.c_size_t, [C.POINTER(FvtgCfg)]),
+    "fvtg_pack_weights": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgParam), i32, vp, C.c_size_t,
+                                C.POINTER(FvtgWeights), vp]),
+    "fvtg_pack_weights_host": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgParam), i32, vp, C.c_size_t, vp,
+                                     C.POINTER(FvtgWeights)]),
     "fvtg_fusion_fwd": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgWeights), C.POINTER(FvtgBatch),
                               C.POINTER(FvtgFusionOut), vp, C.c_size_t, vp]),
     "fvtg_pyramid_heads_fwd": (i32, [C.POINTER(FvtgCfg), C.POINTER(FvtgWeights), i32, i32, vp, vp,

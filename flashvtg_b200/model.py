@@ -401,6 +401,61 @@ class FlashVTGB200(torch.nn.Module):
             self._ws[key] = (slot(), slot())
         return self._ws[key]
 
+    # ------------------------------------------------------ the three kernel groups as separate calls
+    @torch.no_grad()
+    def fusion(self, src_vid: torch.Tensor, vid_len: torch.Tensor, src_txt: torch.Tensor, txt_len: torch.Tensor,
+               uniform_len: bool = False):
+        """Kernel group A alone (fvtg_fusion_fwd; model.py:148-195,213-216): input projections, dummy-token
+        encoder, T2V cross-attention stack, self-attention encoder, saliency head.
+        Returns (video_emb (B,Lv,256), saliency (B,Lv), t2vattn (B,Lv), dummy_tokens (B,nd,256))."""
+        lib = self._lib = self._lib or _lib.load()
+        cfg = self.cfg
+        if not src_vid.is_cuda:
+            raise RuntimeError("FlashVTGB200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        dev = src_vid.device
+        B, Lv, _ = src_vid.shape
+        Lt = src_txt.shape[1]
+        W = self._weights(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        emb, sal, t2v = torch.empty(B, Lv, 256, **f32), torch.empty(B, Lv, **f32), torch.empty(B, Lv, **f32)
+        dummy = torch.empty(B, cfg.num_dummies, 256, **f32)
+        with torch.cuda.device(dev):
+            batch = _lib.FvtgBatch(B, Lv, Lt, int(bool(uniform_len) or B == 1), src_vid.contiguous().data_ptr(),
+                                   src_txt.contiguous().data_ptr(), vid_len.contiguous().data_ptr(),
+                                   txt_len.contiguous().data_ptr())
+            fout = _lib.FvtgFusionOut(emb.data_ptr(), sal.data_ptr(), t2v.data_ptr(), dummy.data_ptr())
+            need = lib.fvtg_workspace_bytes(C.byref(self._cfg_struct), B, Lv, Lt)
+            ws = self._workspace(dev, need)
+            rc = lib.fvtg_fusion_fwd(C.byref(self._cfg_struct), W.ref(), C.byref(batch), C.byref(fout),
+                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "fvtg_fusion_fwd")
+        return emb, sal, t2v, dummy
+
+    @torch.no_grad()
+    def pyramid_heads(self, video_emb: torch.Tensor, vid_len: torch.Tensor):
+        """Kernel group B alone (fvtg_pyramid_heads_fwd; blocks/blocks.py:52-70,90-105, model.py:197-208):
+        Temporal Feature Layering pyramid + class / conf / coord heads on the encoder output.
+        Returns (cls_logit (B,N), conf_logit (B,N), coord (B,N,2))."""
+        lib = self._lib = self._lib or _lib.load()
+        cfg = self.cfg
+        if not video_emb.is_cuda:
+            raise RuntimeError("FlashVTGB200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        dev = video_emb.device
+        B, Lv, _ = video_emb.shape
+        n_max = cfg.num_points(Lv)
+        W = self._weights(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        cls, conf, coord = torch.empty(B, n_max, **f32), torch.empty(B, n_max, **f32), torch.empty(B, n_max, 2, **f32)
+        with torch.cuda.device(dev):
+            hout = _lib.FvtgHeadsOut(n_max, 0, cls.data_ptr(), conf.data_ptr(), coord.data_ptr())
+            need = lib.fvtg_workspace_bytes(C.byref(self._cfg_struct), B, Lv, 1)
+            ws = self._workspace(dev, need)
+            rc = lib.fvtg_pyramid_heads_fwd(C.byref(self._cfg_struct), W.ref(), B, Lv,
+                                            video_emb.contiguous().data_ptr(), vid_len.contiguous().data_ptr(),
+                                            C.byref(hout), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "fvtg_pyramid_heads_fwd")
+        return cls, conf, coord
+
     @torch.no_grad()
     def decode(self, cls_logit: torch.Tensor, conf_logit: torch.Tensor, coord: torch.Tensor,
                vid_len: torch.Tensor, Lv: int, duration: Optional[torch.Tensor] = None,

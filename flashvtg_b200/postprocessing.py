@@ -190,5 +190,11 @@ def compute_hl_results(model, eval_loader, opt=None):
                     video_ap.append(highlight_ap(pred, (cur > med).astype(np.float64), topk=5))
                 aps.append(video_ap)
             else:
+                # quirk kept (inference.py:197-200): for a video without a positive label the reference's
+                # `continue` leaves the per-video loop BEFORE video_ap_collected.append, so the video is left
+                # out of the mean instead of counting as AP 0 (the TVSum branch's `continue` only skips one
+                # annotator and keeps the video)
+                if label.reshape(-1).sum() == 0:
+                    continue
                 aps.append([highlight_ap(pred, label.reshape(-1))])
     return dict(mAP=round(float(np.mean(aps)), 5)) if aps else dict(mAP=0.0)

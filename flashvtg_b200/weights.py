@@ -112,110 +112,50 @@ def pad64(n: int) -> int:
 
 
 class PackedWeights:
-    """Device-resident packed weights + the FvtgWeights struct pointing into them."""
+    """Device-resident packed weights + the FvtgWeights struct pointing into them.
+
+    The packing itself (bf16 K-major operands, conv taps folded into K, LayerNorm / token-type folding) is
+    fvtg_pack_weights in the C-ABI library (csrc/pack.cu): this class only hands it the state_dict as
+    (name, host pointer, numel) triples and owns the one device buffer the result lives in, so a non-Python
+    host loads a checkpoint through exactly the same code."""
 
     def __init__(self, cfg: ModelConfig, sd: dict, device: torch.device):
         self.device = device
-        self._keep: list = []
         self.struct = _lib.FvtgWeights()
-        self.nbytes = 0
-        w = self.struct
+        lib = _lib.load()
+        cs = make_cfg_struct(cfg)
+        self.nbytes = int(lib.fvtg_packed_weights_bytes(C.byref(cs)))
+        if self.nbytes == 0:
+            raise RuntimeError("fvtg_packed_weights_bytes rejected the configuration: "
+                               + lib.fvtg_last_error().decode(errors="replace"))
+        host = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in sd.items()}
+        params = (_lib.FvtgParam * len(host))()
+        self._names = [k.encode() for k in host]            # keep the C strings alive for the call
+        for i, (k, t) in enumerate(host.items()):
+            params[i].name = self._names[i]
+            params[i].data = t.data_ptr()
+            params[i].numel = t.numel()
+        if torch.device(device).type == "cuda":
+            self.buffer = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                rc = lib.fvtg_pack_weights(C.byref(cs), params, len(host), self.buffer.data_ptr(), self.nbytes,
+                                           C.byref(self.struct), _lib.stream_ptr())
+        else:   # layout inspection on the host (tests): same packer, no CUDA call
+            raw = torch.empty(self.nbytes + 256, dtype=torch.uint8)
+            skip = (-raw.data_ptr()) % 256
+            self.buffer = raw[skip:skip + self.nbytes]
+            rc = lib.fvtg_pack_weights_host(C.byref(cs), params, len(host), self.buffer.data_ptr(), self.nbytes,
+                                            None, C.byref(self.struct))
+        _lib.check(rc, "fvtg_pack_weights")
 
-        def f32(t):
-            t = t.detach().to(torch.float32).contiguous().to(device)
-            self._keep.append(t)
-            self.nbytes += t.numel() * 4
-            return t.data_ptr()
-
-        def b16(t, k_pad=None, n_pad=None):
-            t = t.detach().to(torch.float32)
-            n, k = t.shape
-            k_pad = k_pad or pad64(k)
-            n_pad = n_pad or n
-            out = torch.zeros(n_pad, k_pad, dtype=torch.float32)
-            out[:n, :k] = t
-            out = out.to(torch.bfloat16).contiguous().to(device)
-            self._keep.append(out)
-            self.nbytes += out.numel() * 2
-            return out.data_ptr()
-
-        def lin(dst, weight, bias, k_pad=None, n_pad=None):
-            dst.w = b16(weight, k_pad, n_pad)
-            if n_pad and n_pad != bias.numel():
-                bb = torch.zeros(n_pad)
-                bb[: bias.numel()] = bias
-                bias = bb
-            dst.b = f32(bias)
-
-        def ln(dst, prefix):
-            dst.g = f32(sd[prefix + ".weight"])
-            dst.b = f32(sd[prefix + ".bias"])
-
-        te = sd["token_type_embeddings.weight"].float()
-        for name, dst, dim, row in (("input_vid_proj", w.vid, cfg.v_feat_dim, 1),
-                                    ("input_txt_proj", w.txt, cfg.t_feat_dim, 0)):
-            ln(dst.ln0, f"{name}.0.LayerNorm")
-            # LayerNorm(raw dim) folded into the first projection (csrc/inproj.cu):
-            #   LN(x) W^T + b = rstd * ((x - m0) Wg^T - mean(x - m0) * rowsum(Wg)) + (W beta + b)
-            w0 = sd[f"{name}.0.net.1.weight"].float()
-            g0 = sd[f"{name}.0.LayerNorm.weight"].float()
-            b0 = sd[f"{name}.0.LayerNorm.bias"].float()
-            wg = w0 * g0[None, :]
-            lin(dst.fc0, wg, w0 @ b0 + sd[f"{name}.0.net.1.bias"].float(), pad64(dim))
-            dst.fc0_wsum = f32(wg.to(torch.bfloat16).float().sum(1))
-            ln(dst.ln1, f"{name}.1.LayerNorm")
-            # token_type_embeddings row folded into the bias (model.py:151-152)
-            lin(dst.fc1, sd[f"{name}.1.net.1.weight"], sd[f"{name}.1.net.1.bias"].float() + te[row])
-        w.dummy_tok = f32(sd["dummy_rep_token"])
-        w.dummy_pos = f32(sd["dummy_rep_pos"])
-
-        def layer(dst, prefix, in_proj):
-            if in_proj:
-                lin(dst.in_proj, sd[prefix + ".self_attn.in_proj_weight"],
-                    sd[prefix + ".self_attn.in_proj_bias"])
-            lin(dst.out_proj, sd[prefix + ".self_attn.out_proj.weight"],
-                sd[prefix + ".self_attn.out_proj.bias"])
-            ln(dst.norm1, prefix + ".norm1")
-            lin(dst.ff1, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"])
-            lin(dst.ff2, sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"])
-            ln(dst.norm2, prefix + ".norm2")
-            dst.prelu = float(sd[prefix + ".activation.weight"].reshape(-1)[0])
-
-        for i in range(cfg.dummy_layers):
-            layer(w.dummy[i], f"txtproj_encoder.layers.{i}", True)
-        for i in range(cfg.t2v_layers):
-            layer(w.t2v[i], f"transformer.t2v_encoder.layers.{i}", False)
-        for i in range(cfg.enc_layers):
-            layer(w.enc[i], f"transformer.encoder.layers.{i}", True)
-        w.sal_w1 = f32(sd["saliency_proj1.weight"])
-        w.sal_b1 = f32(sd["saliency_proj1.bias"])
-        w.sal_w2t = f32(sd["saliency_proj2.weight"].t())
-        w.sal_b2 = f32(sd["saliency_proj2.bias"])
-        for l in range(1, cfg.num_levels):
-            for j in range(l):
-                cw = sd[f"pyramid.blocks.{l}.{1 + 5 * j}.weight"]      # (out, in, tap)
-                lin(w.pyr[l][j].conv, cw.permute(0, 2, 1).reshape(D, 2 * D),
-                    sd[f"pyramid.blocks.{l}.{1 + 5 * j}.bias"])
-                ln(w.pyr[l][j].ln, f"pyramid.blocks.{l}.{3 + 5 * j}")
-        k = cfg.kernel_size
-        for head, dst in (("class_head", w.cls), ("conf_head", w.conf)):
-            for c in range(cfg.num_conv_layers):
-                cw = sd[f"{head}.convs.{c}.weight"][:, :, 0, :]      # (out, in, tap)
-                lin(dst.conv[c], cw.permute(0, 2, 1).reshape(D, k * D), sd[f"{head}.convs.{c}.bias"])
-            for m in range(cfg.num_mlp_layers - 1):
-                lin(dst.mlp[m], sd[f"{head}.fc.layers.{m}.weight"], sd[f"{head}.fc.layers.{m}.bias"])
-            last = cfg.num_mlp_layers - 1
-            dst.last_w = f32(sd[f"{head}.fc.layers.{last}.weight"].reshape(-1))
-            dst.last_b = float(sd[f"{head}.fc.layers.{last}.bias"].reshape(-1)[0])
-        ck = cfg.coord_kernel
-        lin(w.coord1, sd["coord_head.module.1.weight"].permute(0, 2, 1).reshape(D, ck * D),
-            sd["coord_head.module.1.bias"])
-        lin(w.coord2, sd["coord_head.module.3.weight"].permute(0, 2, 1).reshape(2, ck * D),
-            sd["coord_head.module.3.bias"], n_pad=16)
-        coef = sd["coef"].float().reshape(-1).tolist()
-        for i in range(_lib.MAX_LEVELS):
-            w.coef[i] = coef[i] if i < len(coef) else 1.0
-        w.x = float(sd["x"])
+    def view(self, ptr: int, shape, dtype=torch.float32) -> torch.Tensor:
+        """Tensor view of the packed buffer at address `ptr` (a pointer field of .struct)."""
+        n = 1
+        for d in shape:
+            n *= d
+        off = ptr - self.buffer.data_ptr()
+        esz = torch.empty(0, dtype=dtype).element_size()
+        return self.buffer[off:off + n * esz].view(dtype).view(*shape)
 
     def ref(self):
         return C.byref(self.struct)

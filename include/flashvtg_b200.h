@@ -192,6 +192,29 @@ typedef struct FvtgDecodeOut {
   int32_t* nms_count;  /* [B]: rows in nms_windows (== count except hull mode) */
 } FvtgDecodeOut;
 
+/* ---- checkpoint loading --------------------------------------------------------------------------
+ * The weight ABI of the drop-in is the reference's state_dict (FlashVTG/inference.py:471,
+ * `model.load_state_dict(checkpoint["model"], strict=True)`): one FvtgParam per entry, HOST fp32,
+ * contiguous, under the reference's key name (model.py:81-135, transformer.py:311-330,387-405,
+ * blocks/blocks.py:23-50,93-101).  fvtg_pack_weights converts them into the packed device layout documented
+ * on FvtgLinear / FvtgInProj above (bf16 K-major operands, conv taps folded into K, LayerNorm and token-type
+ * folding) inside ONE caller-owned device buffer of fvtg_packed_weights_bytes(cfg) bytes (256-byte aligned)
+ * and fills `out` with pointers into it; the copy is enqueued on `stream`.  Strict like torch: a missing key,
+ * an unexpected key or a wrong element count returns FVTG_EINVAL with the key in fvtg_last_error(). */
+typedef struct FvtgParam {
+  const char* name;    /* reference state_dict key */
+  const float* data;   /* host fp32, contiguous in the reference's own shape */
+  int64_t numel;
+} FvtgParam;
+size_t fvtg_packed_weights_bytes(const FvtgCfg* cfg);
+int32_t fvtg_pack_weights(const FvtgCfg* cfg, const FvtgParam* params, int32_t n_params, void* device_buf,
+                          size_t device_bytes, FvtgWeights* out, void* stream);
+/* The same packing into a HOST buffer, no CUDA call: `out` points into the address range starting at
+ * target_base (null = host_buf itself), i.e. where the caller will place the bytes (its own device upload,
+ * a memory-mapped weight file, ...). */
+int32_t fvtg_pack_weights_host(const FvtgCfg* cfg, const FvtgParam* params, int32_t n_params, void* host_buf,
+                               size_t host_bytes, const void* target_base, FvtgWeights* out);
+
 size_t fvtg_workspace_bytes(const FvtgCfg* cfg, int32_t B, int32_t Lv, int32_t Lt);
 /* Videos processed per internal chunk (sized so a chunk's activations stay L2 resident). */
 int32_t fvtg_chunk_videos(const FvtgCfg* cfg, int32_t Lv, int32_t Lt);

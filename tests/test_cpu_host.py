@@ -150,24 +150,50 @@ def test_packed_layouts_fold_taps_and_token_type():
     cfg = PRESETS["qvh_iv2"]
     sd = synth.make_state_dict(cfg, 3, spread=True)
     W = PackedWeights(cfg, sd, torch.device("cpu"))
-    by_ptr = {t.data_ptr(): t for t in W._keep}
-    conv = by_ptr[W.struct.cls.conv[0].w].float()                  # [256][k*256], tap-major K
+    k = cfg.kernel_size
+    conv = W.view(W.struct.cls.conv[0].w, (256, k * 256), torch.bfloat16).float()   # [256][k*256], tap-major K
     ref = sd["class_head.convs.0.weight"][:, :, 0, :].permute(0, 2, 1).reshape(256, -1)
     assert torch.allclose(conv, ref.to(torch.bfloat16).float())
-    pyr = by_ptr[W.struct.pyr[2][1].conv.w].float()
+    pyr = W.view(W.struct.pyr[2][1].conv.w, (256, 512), torch.bfloat16).float()
     ref = sd["pyramid.blocks.2.6.weight"].permute(0, 2, 1).reshape(256, 512)
     assert torch.allclose(pyr, ref.to(torch.bfloat16).float())
-    b = by_ptr[W.struct.vid.fc1.b]
+    b = W.view(W.struct.vid.fc1.b, (256,))
     assert torch.allclose(b, sd["input_vid_proj.1.net.1.bias"] + sd["token_type_embeddings.weight"][1])
-    fc0 = by_ptr[W.struct.vid.fc0.w]
-    assert fc0.shape == (256, 832) and float(fc0[:, 770:].abs().sum()) == 0.0
+    fc0 = W.view(W.struct.vid.fc0.w, (256, 832), torch.bfloat16)
+    assert float(fc0[:, 770:].float().abs().sum()) == 0.0
     # LayerNorm over the raw dim is folded into the first projection (csrc/inproj.cu)
     w0, g0, b0 = (sd[f"input_vid_proj.0.{n}"] for n in ("net.1.weight", "LayerNorm.weight", "LayerNorm.bias"))
     assert torch.equal(fc0[:, :770].float(), (w0 * g0[None, :]).to(torch.bfloat16).float())
-    assert torch.allclose(by_ptr[W.struct.vid.fc0.b], w0 @ b0 + sd["input_vid_proj.0.net.1.bias"], atol=1e-6)
-    assert torch.allclose(by_ptr[W.struct.vid.fc0_wsum], fc0.float().sum(1), atol=1e-5)
-    c2 = by_ptr[W.struct.coord2.w]
-    assert c2.shape == (16, 768) and float(c2[2:].abs().sum()) == 0.0
+    assert torch.allclose(W.view(W.struct.vid.fc0.b, (256,)), w0 @ b0 + sd["input_vid_proj.0.net.1.bias"], atol=1e-6)
+    assert torch.allclose(W.view(W.struct.vid.fc0_wsum, (256,)), fc0.float().sum(1), atol=1e-5)
+    c2 = W.view(W.struct.coord2.w, (16, 768), torch.bfloat16).float()
+    assert float(c2[2:].abs().sum()) == 0.0
+    ref = sd["coord_head.module.3.weight"].permute(0, 2, 1).reshape(2, 768)
+    assert torch.equal(c2[:2], ref.to(torch.bfloat16).float())
+    assert torch.equal(W.view(W.struct.sal_w2t, (256, 256)), sd["saliency_proj2.weight"].t().contiguous())
+    assert W.struct.t2v[0].in_proj.w is None and W.struct.enc[0].in_proj.w is not None
+
+
+def test_pack_weights_is_strict_like_torch():
+    """fvtg_pack_weights (the C-ABI checkpoint loader) rejects a missing key, an unexpected key and a wrong
+    element count, naming the key - the strict=True behaviour of inference.py:471."""
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS
+    from flashvtg_b200.weights import PackedWeights
+    cfg = PRESETS["qvh_iv2"]
+    sd = synth.make_state_dict(cfg, 3)
+    bad = dict(sd)
+    bad.pop("class_head.convs.0.bias")
+    with pytest.raises(RuntimeError, match="Missing key.*class_head.convs.0.bias"):
+        PackedWeights(cfg, bad, torch.device("cpu"))
+    bad = dict(sd)
+    bad["extra.weight"] = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="Unexpected key.*extra.weight"):
+        PackedWeights(cfg, bad, torch.device("cpu"))
+    bad = dict(sd)
+    bad["coef"] = torch.ones(3)
+    with pytest.raises(RuntimeError, match="size mismatch for coef"):
+        PackedWeights(cfg, bad, torch.device("cpu"))
 
 
 def test_config_presets_and_point_counts():

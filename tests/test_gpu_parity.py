@@ -165,9 +165,11 @@ def test_forward_matches_oracle_and_golden(entry):
         scale = np.abs(spans_all).max()
         gs = torch.sigmoid(got_logit).numpy()
         for row in r.boundary[b, :cnt].cpu().numpy():
-            j = int(np.argmin(np.abs(gs - row[2])))
-            assert abs(gs[j] - row[2]) < 1e-6
-            assert np.abs(spans_all[j] - row[:2]).max() < TOL * scale
+            # the point(s) whose score this row carries: saturated sigmoids tie exactly (spread-init fixtures),
+            # so the row must match the span of ONE of the points with that score
+            cand = np.nonzero(np.abs(gs - row[2]) < 1e-6)[0]
+            assert cand.size > 0
+            assert min(np.abs(spans_all[j] - row[:2]).max() for j in cand) < TOL * scale
 
 
 @pytest.mark.parametrize("entry", load_forward_index(), ids=lambda e: e["file"][:-4])
@@ -364,6 +366,22 @@ def test_full_size_properties_b1024():
     out2, order2, _ = temporal_nms(rb.nms_windows, rb.nms_count, cfg.nms_thd, "normal")
     assert torch.equal(out2, rb.nms_windows)
     assert rb.launches > 0
+    # ... and the B = 1024 run itself against the oracle (not only against the small run): the 8 seed videos,
+    # read from three different chunk positions of the big batch, within the north_star tolerance
+    from oracle import forward as O
+    outs = O.forward_batch(sd, cfg, small)
+    x = float(sd["x"])
+    for k in (0, 63, rep - 1):
+        for b, o in enumerate(outs):
+            g = k * 8 + b
+            lv, n = int(small["vid_len"][b]), o["logit"].shape[0]
+            logit = x * rb.cls_logit[g, :n].cpu() + (1 - x) * rb.conf_logit[g, :n].cpu()
+            for name, got, want in (("saliency", rb.saliency[g, :lv].cpu(), o["saliency"]),
+                                    ("t2vattn", rb.t2vattn[g, :lv].cpu(), o["t2vattn"]),
+                                    ("score", torch.sigmoid(logit), o["score"]),
+                                    ("coord", rb.coord[g, :n].cpu(), o["coord"])):
+                e = max_rel(got.numpy(), want.numpy())
+                assert e < TOL, f"B=1024 video {g} {name}: max-norm rel err {e:.3e} vs the oracle"
 
 
 def test_infer_host_pipeline_equals_device_call():
@@ -548,3 +566,82 @@ torch.save({"cls": r.cls_logit.cpu(), "conf": r.conf_logit.cpu(), "coord": r.coo
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
     assert torch.equal(outs[1]["cls"], ref["cls_logit"].cpu())
+
+
+def test_torch_ops_and_standalone_stage_chain_equal_the_fused_forward():
+    """Every torch.ops.fvtg.* operator (flashvtg_b200/ops.py) is callable, and the standalone
+    C-ABI chain fvtg_fusion_fwd -> fvtg_pyramid_heads_fwd -> fvtg_decode_nms (the three kernel groups as separate
+    calls) equals fvtg_forward bit for bit: same kernels, same launch parameters, only the entry point differs."""
+    import flashvtg_b200.ops as ops
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS
+    cfg = PRESETS["qvh_iv2"]
+    sd = synth.make_state_dict(cfg, 2025, spread=True)
+    dev = torch.device("cuda:0")
+    m = _model(cfg, sd)
+    h = ops.register_model(m)
+    b = synth.make_inputs(cfg, 5, 75, 32, seed=21, ragged=True, min_lv=9)
+    d = {k: v.to(dev) for k, v in b.items()}
+    r = m.infer(d["src_vid"], d["vid_len"], d["src_txt"], d["txt_len"], duration=d["duration"], nms="normal",
+                want_heads=True, want_emb=True, want_dummy=True)
+    emb, sal, t2v, dummy = torch.ops.fvtg.fusion_fwd(d["src_vid"], d["vid_len"], d["src_txt"], d["txt_len"], h)
+    assert torch.equal(sal, r.saliency) and torch.equal(t2v, r.t2vattn)
+    assert torch.equal(emb, r.video_emb) and torch.equal(dummy, r.dummy_tokens)
+    cls, conf, coord = torch.ops.fvtg.pyramid_heads_fwd(emb, d["vid_len"], h)
+    assert torch.equal(cls, r.cls_logit) and torch.equal(conf, r.conf_logit) and torch.equal(coord, r.coord)
+    bnd, win, nms_w, nms_o, cnt, nms_c = torch.ops.fvtg.decode_nms(cls, conf, coord, d["vid_len"], d["duration"],
+                                                                  75, h, 0, cfg.nms_thd)
+    assert torch.equal(cnt, r.count) and torch.equal(nms_c, r.nms_count)
+    for bi in range(5):
+        n = int(cnt[bi])
+        assert torch.equal(bnd[bi, :n], r.boundary[bi, :n]) and torch.equal(win[bi, :n], r.windows[bi, :n])
+        assert torch.equal(nms_w[bi, :n], r.nms_windows[bi, :n]) and torch.equal(nms_o[bi, :n], r.nms_order[bi, :n])
+    out = torch.ops.fvtg.forward(d["src_vid"], d["vid_len"], d["src_txt"], d["txt_len"], d["duration"], h, 0,
+                                 cfg.nms_thd)
+    assert torch.equal(out[0], r.saliency) and torch.equal(out[4], r.count)
+    for bi in range(5):
+        n = int(cnt[bi])
+        assert torch.equal(out[2][bi, :n], r.boundary[bi, :n]) and torch.equal(out[5][bi, :n], r.nms_windows[bi, :n])
+    w2, o2, c2 = torch.ops.fvtg.temporal_nms(r.windows, r.count, cfg.nms_thd, 0, 100)
+    for bi in range(5):
+        n = int(cnt[bi])
+        assert torch.equal(w2[bi, :n], r.nms_windows[bi, :n]) and torch.equal(o2[bi, :n], r.nms_order[bi, :n])
+    with pytest.raises(NotImplementedError):
+        torch.ops.fvtg.temporal_nms(r.windows.cpu(), r.count.cpu(), 0.7, 0, 100)   # no CPU implementation
+
+
+def test_compute_mr_results_matches_the_oracle_post_processing():
+    """flashvtg_b200.postprocessing.compute_mr_results (forward + compose + PostProcessorDETR
+    [+ NMS] in one device pass) against the oracle's restatement of inference.py:232-355 applied to the SAME
+    device boundaries: every submission row identical."""
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS, postprocessor_preset
+    from flashvtg_b200.postprocessing import compute_mr_results
+    from oracle import postproc as P
+    cfg = PRESETS["qvh_iv2"]
+    sd = synth.make_state_dict(cfg, 2025, spread=True)
+    dev = torch.device("cuda:0")
+    m = _model(cfg, sd)
+    b = synth.make_inputs(cfg, 6, 75, 32, seed=31, ragged=True, min_lv=5)
+    inp = {k: b[k].to(dev) for k in ("src_vid", "src_vid_mask", "src_txt", "src_txt_mask")}
+    metas = [dict(qid=i, query="q", vid=f"v{i}", duration=float(b["duration"][i])) for i in range(6)]
+    clip_ts, mn, mx, rnd = postprocessor_preset(cfg)
+    r = m.infer(inp["src_vid"], b["vid_len"].to(dev), inp["src_txt"], b["txt_len"].to(dev),
+                duration=b["duration"].to(dev), nms=None)
+    for nms in (None, "normal"):
+        got = compute_mr_results(m, [(metas, inp)], nms=nms)
+        assert [g["qid"] for g in got] == list(range(6))
+        for i, g in enumerate(got):
+            n = int(r.count[i])
+            w, out, _ = P.full_postproc(r.boundary[i, :n].cpu().numpy(), metas[i]["duration"], cfg.clip_length,
+                                        clip_ts, mn, mx, rnd, cfg.nms_thd, "normal")
+            want = np.asarray(out if nms else w, np.float64)
+            have = np.asarray(g["pred_relevant_windows"], np.float64)
+            assert have.shape == want.shape
+            if nms:
+                assert np.array_equal(have.astype(np.float32), want.astype(np.float32))
+            else:
+                assert np.array_equal(have, want)
+            lv = int(b["vid_len"][i])
+            sal = np.rint(r.saliency[i, :lv].cpu().numpy().astype(np.float64) * 1e4) / 1e4
+            assert np.array_equal(np.asarray(g["pred_saliency_scores"]), sal)

@@ -97,3 +97,31 @@ def test_compute_hl_results_runs_and_ranks_like_the_oracle():
             va.append(highlight_ap(o["saliency"].numpy(), (cur > cur.median()).double().numpy(), 5))
         aps.append(va)
     assert abs(got["mAP"] - round(float(np.mean(aps)), 5)) < 0.05   # bf16 saliency may swap near-ties
+
+
+@pytest.mark.gpu
+def test_youtube_uni_video_without_positive_label_is_left_out_of_the_mean():
+    """inference.py:197-200: the youtube_uni branch `continue`s before video_ap_collected.append when a video has no
+    positive label, so that video does not count as AP 0 - it is dropped from the mean."""
+    from flashvtg_b200 import synth
+    from flashvtg_b200.config import PRESETS
+    from flashvtg_b200.model import FlashVTGB200
+    from flashvtg_b200.postprocessing import compute_hl_results, highlight_ap
+    cfg = PRESETS["youtube_uni"]
+    sd = synth.make_state_dict(cfg, 2025, spread=True)
+    batch = synth.make_inputs(cfg, 3, 40, 4, seed=6, ragged=False)
+    dev = torch.device("cuda:0")
+    m = FlashVTGB200(cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    rng = np.random.Generator(np.random.PCG64(3))
+    metas = [{"label": (rng.random((40, 1)) > 0.5).astype(np.float64).tolist()},
+             {"label": np.zeros((40, 1)).tolist()},                                  # no positive clip
+             {"label": (rng.random((40, 1)) > 0.5).astype(np.float64).tolist()}]
+    inp = {k: batch[k].to(dev) for k in ("src_vid", "src_vid_mask", "src_txt", "src_txt_mask")}
+    got = compute_hl_results(m, [(metas, inp)])
+    r = m.infer(inp["src_vid"], inp["src_vid_mask"].sum(1).int(), inp["src_txt"], inp["src_txt_mask"].sum(1).int(),
+                nms=None)
+    sal = r.saliency.cpu().numpy()
+    want = np.mean([[highlight_ap(sal[i], np.asarray(metas[i]["label"]).reshape(-1))] for i in (0, 2)])
+    assert got["mAP"] == round(float(want), 5)
+    assert compute_hl_results(m, [([metas[1]], {k: v[1:2] for k, v in inp.items()})]) == dict(mAP=0.0)
