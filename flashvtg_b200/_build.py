@@ -18,6 +18,10 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libflashvtg_b200.so"
 OBJ_DIR = PKG_DIR / "build"
 STAMP = PKG_DIR / "build" / "sources.sha256"
+# the debug flavour: the same sources with -DFVTG_DEBUG_HOOKS (fvtg_dbg_* test / trace hooks + csrc/probe.cu
+# micro-benchmarks); loaded only by the kernel-level unit tests and tools/, never by the product path
+DBG_LIB_PATH = PKG_DIR / "libflashvtg_b200_dbg.so"
+DBG_OBJ_DIR = PKG_DIR / "build" / "dbg"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,7 +43,7 @@ def _sources() -> list[Path]:
 def _digest() -> str:
     h = hashlib.sha256()
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) +
-                    [PKG_DIR.parent / "include" / "flashvtg_b200.h"]):
+                    [PKG_DIR.parent / "include" / "flashvtg_b200.h", PKG_DIR.parent / "include" / "flashvtg_b200_dbg.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -47,34 +51,43 @@ def _digest() -> str:
 
 
 def is_fresh() -> bool:
-    return LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == _digest()
+    return (LIB_PATH.exists() and DBG_LIB_PATH.exists() and STAMP.exists()
+            and STAMP.read_text().strip() == _digest())
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every csrc/*.cu for sm_100a and link libflashvtg_b200.so in-tree."""
+    """Compile every csrc/*.cu for sm_100a and link libflashvtg_b200.so (the product) and
+    libflashvtg_b200_dbg.so (product + debug hooks + probes) in-tree."""
     if not force and is_fresh():
         return LIB_PATH
     OBJ_DIR.mkdir(exist_ok=True)
+    DBG_OBJ_DIR.mkdir(exist_ok=True)
     nvcc = _nvcc()
     srcs = _sources()
 
-    def compile_one(src: Path) -> Path:
-        obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", str(src), "-o", str(obj)]
+    def compile_one(job) -> Path:
+        src, dbg = job
+        odir = DBG_OBJ_DIR if dbg else OBJ_DIR
+        obj = odir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DFVTG_DEBUG_HOOKS"] if dbg else []), "-Xptxas", "-v", "-c", str(src),
+               "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
-        (OBJ_DIR / (src.stem + ".ptxas.log")).write_text(r.stderr)
-        if verbose:
+        (odir / (src.stem + ".ptxas.log")).write_text(r.stderr)
+        if verbose and not dbg:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "shared"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    jobs = [(s, False) for s in srcs if s.stem != "probe"] + [(s, True) for s in srcs]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        objs = list(ex.map(compile_one, jobs))
+    for lib, sel in ((LIB_PATH, [o for o, j in zip(objs, jobs) if not j[1]]),
+                     (DBG_LIB_PATH, [o for o, j in zip(objs, jobs) if j[1]])):
+        cmd = [nvcc, "-shared", "-o", str(lib), *map(str, sel), "-cudart", "shared"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     STAMP.write_text(_digest())
     return LIB_PATH
 

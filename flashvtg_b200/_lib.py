@@ -147,21 +147,30 @@ SIGNATURES = {
     "fvtg_last_launch_count": (C.c_int64, []),
     "fvtg_last_error": (C.c_char_p, []),
     "fvtg_abi_version": (i32, []),
-    "fvtg_dbg_set_trace": (None, [vp]),
     "fvtg_prof_enable": (None, [i32]),
     "fvtg_prof_collect": (i32, [vp, vp, i32]),
+}
+# include/flashvtg_b200_dbg.h: only in libflashvtg_b200_dbg.so (product sources + -DFVTG_DEBUG_HOOKS + probe.cu)
+DBG_SIGNATURES = {
+    "fvtg_dbg_set_trace": (None, [vp]),
     "fvtg_dbg_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "fvtg_dbg_stream_probe": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "fvtg_dbg_inproj": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "fvtg_dbg_mufu_probe": (i32, [i32, i32, vp, vp]),
 }
+DBG_LIB_PATH = PKG_DIR / "libflashvtg_b200_dbg.so"
 
 _lib = None
+_dbg = None
 
 
 def load() -> C.CDLL:
     """Load libflashvtg_b200.so (built in-tree by flashvtg_b200._build / __graft_entry__.build)."""
     global _lib
     if _lib is not None:
+        return _lib
+    if os.environ.get("FVTG_DEBUG_LIB", "0") not in ("", "0"):
+        _lib = load_debug()   # tools/trace_*.py: the whole path through the hook-carrying build
         return _lib
     if not LIB_PATH.exists():
         raise RuntimeError(
@@ -183,9 +192,26 @@ def load() -> C.CDLL:
     return lib
 
 
-def check(rc: int, what: str) -> None:
+def load_debug() -> C.CDLL:
+    """libflashvtg_b200_dbg.so: every product symbol plus the fvtg_dbg_* hooks (kernel-level unit tests, tools/)."""
+    global _dbg
+    if _dbg is not None:
+        return _dbg
+    if not DBG_LIB_PATH.exists():
+        raise RuntimeError(f"{DBG_LIB_PATH} is missing: run `python -m flashvtg_b200._build` (needs nvcc)")
+    import torch  # noqa: F401
+    lib = C.CDLL(str(DBG_LIB_PATH))
+    for name, (res, args) in {**SIGNATURES, **DBG_SIGNATURES}.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _dbg = lib
+    return lib
+
+
+def check(rc: int, what: str, lib=None) -> None:
     if rc != OK:
-        msg = load().fvtg_last_error().decode(errors="replace")
+        msg = (lib or load()).fvtg_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 

@@ -28,9 +28,11 @@ static ProfState& prof_state() {
   static thread_local ProfState s;
   return s;
 }
+#ifdef FVTG_DEBUG_HOOKS
 static thread_local long long* g_trace = nullptr;
 long long* dbg_trace() { return g_trace; }
 void set_dbg_trace(long long* p) { g_trace = p; }
+#endif
 bool prof_on() { return prof_state().on; }
 static cudaEvent_t prof_event() {
   ProfState& p = prof_state();
@@ -157,7 +159,9 @@ const char* fvtg_last_error(void) { return fvtg::host_state().err; }
 int64_t fvtg_last_launch_count(void) { return fvtg::host_state().launches; }
 int32_t fvtg_abi_version(void) { return FVTG_ABI_VERSION; }
 
+#ifdef FVTG_DEBUG_HOOKS
 void fvtg_dbg_set_trace(void* device_buf) { fvtg::set_dbg_trace(static_cast<long long*>(device_buf)); }
+#endif
 
 void fvtg_prof_enable(int32_t on) { fvtg::prof_state().on = on != 0; }
 

@@ -54,8 +54,15 @@ inline void count_launch(int n = 1) { host_state().launches += n; }
 // kernel with a CUDA event pair on the launching stream, so bench.py can time each kernel class
 // live (the roofline numerator) without a profiler attached.  Off by default: zero cost.
 enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LNCAST = 2, PC_DECODE = 3, PC_OTHER = 4, PC_LAYER = 5, PC_COUNT = 6 };
+// Debug build only (libflashvtg_b200_dbg.so, -DFVTG_DEBUG_HOOKS): the device buffer registered with
+// fvtg_dbg_set_trace (>= 4096 int64) that kernels stamp with clock64; the product library has no such hook
+// and every kernel's trace pointer is a constant null.
+#ifdef FVTG_DEBUG_HOOKS
 void set_dbg_trace(long long* p);
-long long* dbg_trace();  // device buffer registered with fvtg_dbg_set_trace (>= 4096 int64), or null
+long long* dbg_trace();
+#else
+inline long long* dbg_trace() { return nullptr; }
+#endif
 bool prof_on();
 void prof_begin(cudaStream_t st, int cls);
 void prof_end(cudaStream_t st);

@@ -663,6 +663,7 @@ int launch_gemm(cudaStream_t st, const void* a, const void* a2, uint64_t a_rows,
 
 }  // namespace fvtg
 
+#ifdef FVTG_DEBUG_HOOKS   // test / tuning hook: only in libflashvtg_b200_dbg.so
 extern "C" int32_t fvtg_dbg_gemm(const void* a, const void* w, const float* bias, float* out,
                                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream) {
   using namespace fvtg;
@@ -686,3 +687,4 @@ extern "C" int32_t fvtg_dbg_gemm(const void* a, const void* w, const float* bias
   }
   return launch_gemm(static_cast<cudaStream_t>(stream), a, nullptr, M, K, K, w, g);
 }
+#endif

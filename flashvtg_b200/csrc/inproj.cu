@@ -338,9 +338,11 @@ int launch_inproj(cudaStream_t st, const float* x, int rows, int dim, int dim_pa
 }  // namespace fvtg
 
 // debug / tuning entry: the fused first projection alone (tools/trace_inproj.py)
+#ifdef FVTG_DEBUG_HOOKS   // test / tuning hook: only in libflashvtg_b200_dbg.so
 extern "C" int32_t fvtg_dbg_inproj(const float* x, int32_t rows, int32_t dim, int32_t dim_pad, const void* wg,
                                    const float* wsum, const float* cfold, const float* g1, const float* b1,
                                    void* out, void* stream) {
   return fvtg::launch_inproj(static_cast<cudaStream_t>(stream), x, rows, dim, dim_pad, wg, wsum, cfold, g1, b1,
                              static_cast<fvtg::bf16*>(out));
 }
+#endif

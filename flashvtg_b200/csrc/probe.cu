@@ -1,3 +1,4 @@
+#ifdef FVTG_DEBUG_HOOKS   // micro-benchmarks: compiled into libflashvtg_b200_dbg.so only, never into the product library
 // Debug probes (not on the product path), run by tools/probe_tma.py on a B200:
 //  * fvtg_dbg_tma_probe: how fast can every SM stream the SAME weight matrix from L2 into a
 //    shared-memory ring of `stages` units with no consumer work?  mode 0: 2-D tensor boxes
@@ -419,3 +420,50 @@ extern "C" int32_t fvtg_dbg_stream_probe(const float* x, int32_t rows, int32_t d
   FVTG_LAUNCH_CHECK("stream_probe_kernel");
   return FVTG_OK;
 }
+
+// fvtg_dbg_mufu_probe: throughput of ex2.approx (MUFU) against fma (the issue-rate reference), per SM sub-partition.
+namespace fvtg {
+__global__ void mufu_probe_kernel(int iters, float* out) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = -0.001f * (threadIdx.x + i + 1);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+  }
+  long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += x[i];
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = 1.f + 1e-3f * (threadIdx.x + i);
+  __syncthreads();
+  long long t2 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(y[i]) : "f"(0.999f), "f"(1e-4f));
+  }
+  long long t3 = clock64();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += y[i];
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // warps per sub-partition = blockDim / 128; cycles per warp-instruction on one sub-partition
+    const float per_smsp = static_cast<float>(blockDim.x) / 128.f;
+    out[0] = static_cast<float>(t1 - t0) / (8.f * iters * fmaxf(per_smsp, 1.f));
+    out[1] = static_cast<float>(t3 - t2) / (8.f * iters * fmaxf(per_smsp, 1.f));
+    out[2] = acc;
+  }
+}
+}  // namespace fvtg
+extern "C" int32_t fvtg_dbg_mufu_probe(int32_t warps, int32_t iters, float* out, void* stream) {
+  using namespace fvtg;
+  if (warps < 1 || warps > 32 || iters < 1) return fail(FVTG_EINVAL, "mufu_probe: warps 1..32");
+  mufu_probe_kernel<<<148, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(iters, out);
+  FVTG_LAUNCH_CHECK("mufu_probe_kernel");
+  return FVTG_OK;
+}
+
+#endif  // FVTG_DEBUG_HOOKS

@@ -25,3 +25,12 @@ def lib():
     from flashvtg_b200 import _build, _lib
     _build.build()
     return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def dbg_lib():
+    """libflashvtg_b200_dbg.so: the product sources compiled with -DFVTG_DEBUG_HOOKS (+ probe.cu) - the kernel-level
+    unit tests reach single kernels through its fvtg_dbg_* hooks; the product library exports none of them."""
+    from flashvtg_b200 import _build, _lib
+    _build.build()
+    return _lib.load_debug()

@@ -32,6 +32,15 @@ def test_library_exports_every_declared_symbol(lib):
     nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True)
     exported = set(re.findall(r"\b(fvtg_[a-z0-9_]+)\b", nm.stdout))
     assert set(syms) <= exported
+    # debug / test hooks and the probe micro-benchmarks live in the debug flavour only
+    assert not [s for s in exported if s.startswith("fvtg_dbg_")], "debug hooks leaked into the product library"
+    dbg_text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "flashvtg_b200_dbg.h")).read(), flags=re.S)
+    dbg_syms = sorted(set(re.findall(r"\b(fvtg_dbg_[a-z0-9_]+)\s*\(", dbg_text)))
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.DBG_LIB_PATH)], capture_output=True, text=True)
+    dbg_exported = set(re.findall(r"\b(fvtg_[a-z0-9_]+)\b", nm.stdout))
+    assert set(dbg_syms) <= dbg_exported and set(syms) <= dbg_exported
+    for s in dbg_syms:
+        assert s in _lib.DBG_SIGNATURES, f"{s} has no ctypes signature in flashvtg_b200/_lib.py"
 
 
 def test_ctypes_structs_match_the_c_header():

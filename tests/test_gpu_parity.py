@@ -49,7 +49,8 @@ def test_library_loaded_and_native(lib):
     assert os.path.exists(L.LIB_PATH)
 
 
-def test_gemm_against_torch(lib):
+def test_gemm_against_torch(dbg_lib):
+    lib = dbg_lib
     import ctypes as C
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -72,7 +73,8 @@ def test_gemm_against_torch(lib):
     del C
 
 
-def test_first_projection_kernel_against_torch(lib):
+def test_first_projection_kernel_against_torch(dbg_lib):
+    lib = dbg_lib
     """inproj_kernel alone (LayerNorm(raw dim) folded into the GEMM, ReLU, LayerNorm(256)) against an fp64
     torch restatement: ragged feature dims (tail k-block), row counts off the tile size, features with a
     large common offset (the per-row shift that keeps the folded LayerNorm's cancellation benign)."""

@@ -15,7 +15,7 @@ from flashvtg_b200 import _lib  # noqa: E402
 
 
 def main():
-    lib = C.CDLL(str(_lib.LIB_PATH))
+    lib = _lib.load_debug()
     lib.fvtg_dbg_gemm.restype = C.c_int32
     lib.fvtg_dbg_gemm.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]
     lib.fvtg_last_error.restype = C.c_char_p

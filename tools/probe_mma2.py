@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flashvtg_b200 import _lib  # noqa: E402
 
-lib = C.CDLL(str(_lib.LIB_PATH))
+lib = _lib.load_debug()
 lib.fvtg_dbg_mma_probe2.restype = C.c_int32
 lib.fvtg_dbg_mma_probe2.argtypes = [C.c_int32] * 5 + [C.c_void_p, C.c_void_p]
 lib.fvtg_last_error.restype = C.c_char_p

@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flashvtg_b200 import _lib  # noqa: E402
 
-lib = C.CDLL(str(_lib.LIB_PATH))
+lib = _lib.load_debug()
 lib.fvtg_dbg_tma_probe.restype = C.c_int32
 lib.fvtg_dbg_tma_probe.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]

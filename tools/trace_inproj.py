@@ -5,6 +5,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("FVTG_DEBUG_LIB", "1")   # the hook-carrying build (libflashvtg_b200_dbg.so)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flashvtg_b200 import _lib  # noqa: E402
 
