@@ -429,19 +429,35 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_wait();
         const float* bb = s_b1 + p * 128 + qt * 32;
         uint32_t hp[16];
+        const uint64_t al2 = f2_pack(g.prelu, g.prelu);
+        if (g.prelu >= 0.f && g.prelu <= 1.f) {   // PReLU(x) = max(x, a x) for 0 <= a <= 1: no compare / select
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = ld_f4(bb + 4 * i);
-          float x0 = __uint_as_float(u[4 * i + 0]) + b.x;
-          float x1 = __uint_as_float(u[4 * i + 1]) + b.y;
-          float x2 = __uint_as_float(u[4 * i + 2]) + b.z;
-          float x3 = __uint_as_float(u[4 * i + 3]) + b.w;
-          x0 = x0 > 0.f ? x0 : g.prelu * x0;
-          x1 = x1 > 0.f ? x1 : g.prelu * x1;
-          x2 = x2 > 0.f ? x2 : g.prelu * x2;
-          x3 = x3 > 0.f ? x3 : g.prelu * x3;
-          hp[2 * i + 0] = pack_bf16(x0, x1);
-          hp[2 * i + 1] = pack_bf16(x2, x3);
+          for (int i = 0; i < 8; ++i) {
+            const ulonglong2 b = ld_p4(bb + 4 * i);
+            const uint64_t x0 = f2_add(pk2(u, 2 * i), b.x), x1 = f2_add(pk2(u, 2 * i + 1), b.y);
+            float a0, a1, a2, a3, m0, m1, m2, m3;
+            f2_unpack(x0, a0, a1);
+            f2_unpack(x1, a2, a3);
+            f2_unpack(f2_mul(x0, al2), m0, m1);
+            f2_unpack(f2_mul(x1, al2), m2, m3);
+            hp[2 * i + 0] = pack_bf16(fmaxf(a0, m0), fmaxf(a1, m1));
+            hp[2 * i + 1] = pack_bf16(fmaxf(a2, m2), fmaxf(a3, m3));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = ld_f4(bb + 4 * i);
+            float x0 = __uint_as_float(u[4 * i + 0]) + b.x;
+            float x1 = __uint_as_float(u[4 * i + 1]) + b.y;
+            float x2 = __uint_as_float(u[4 * i + 2]) + b.z;
+            float x3 = __uint_as_float(u[4 * i + 3]) + b.w;
+            x0 = x0 > 0.f ? x0 : g.prelu * x0;
+            x1 = x1 > 0.f ? x1 : g.prelu * x1;
+            x2 = x2 > 0.f ? x2 : g.prelu * x2;
+            x3 = x3 > 0.f ? x3 : g.prelu * x3;
+            hp[2 * i + 0] = pack_bf16(x0, x1);
+            hp[2 * i + 1] = pack_bf16(x2, x3);
+          }
         }
         tmem_st16(ha, hp);
         tmem_st_wait();
