@@ -449,7 +449,22 @@ __global__ void mufu_probe_kernel(int iters, float* out) {
   long long t3 = clock64();
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc += y[i];
+  // cvt.rn.bf16x2.f32 (F2FP.BF16.F32.PACK_AB): 8 independent chains, the packed result re-enters as a float
+  uint32_t z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z[i] = __float_as_uint(1.f + 1e-3f * (threadIdx.x + i));
+  __syncthreads();
+  long long t4 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(z[i]) : "f"(__uint_as_float(z[i])), "f"(__uint_as_float(z[(i + 1) & 7])));
+  }
+  long long t5 = clock64();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += __uint_as_float(z[i]);
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out[3] = static_cast<float>(t5 - t4) / (8.f * iters * fmaxf(static_cast<float>(blockDim.x) / 128.f, 1.f));
     // warps per sub-partition = blockDim / 128; cycles per warp-instruction on one sub-partition
     const float per_smsp = static_cast<float>(blockDim.x) / 128.f;
     out[0] = static_cast<float>(t1 - t0) / (8.f * iters * fmaxf(per_smsp, 1.f));

@@ -18,4 +18,5 @@ for warps in (4, 8, 16, 32):
     torch.cuda.synchronize()
     o = out.cpu().tolist()
     print(f"{warps:2d} warps/SM: ex2.approx {o[0]:.2f} cycles per warp instruction per sub-partition "
-          f"(= {32 / o[0]:.2f} lanes/clk/SMSP, {4 * 32 / o[0]:.1f} per SM), fma {o[1]:.2f} cycles")
+          f"(= {32 / o[0]:.2f} lanes/clk/SMSP, {4 * 32 / o[0]:.1f} per SM), fma {o[1]:.2f} cycles, "
+          f"cvt.rn.bf16x2.f32 {o[3]:.2f} cycles")
