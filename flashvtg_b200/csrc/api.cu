@@ -468,7 +468,9 @@ static int prep_ws(const FvtgCfg* cfg, int B, int Lv, int Lt, void* workspace, s
 
 static int check_shapes(const FvtgCfg* cfg, int B, int Lv, int Lt) {
   if (B < 1 || Lv < 1 || Lt < 1) return fail(FVTG_EINVAL, "B, Lv, Lt must be positive");
-  if (Lv > 1024) return fail(FVTG_EINVAL, "Lv %d exceeds the 1024-clip buffer (generator.py:60)", Lv);
+  // kernel limit (row-space geometry, top-k candidate buffers); the reference's own bound is cfg.buffer_size
+  // (generator.py:60), which the host checks - for the highlight presets (buffer 2048) this limit is the tighter one
+  if (Lv > 1024) return fail(FVTG_EINVAL, "Lv %d exceeds the 1024 clips per video the kernels support", Lv);
   if (cfg->num_dummies + Lt > 1024) return fail(FVTG_EINVAL, "num_dummies + Lt too large");
   return FVTG_OK;
 }

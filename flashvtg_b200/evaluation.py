@@ -210,12 +210,16 @@ def eval_predictions(windows: torch.Tensor, counts: torch.Tensor, saliency: Opti
     """Metrics straight from the device-resident outputs of `FlashVTGB200.infer` - ranked windows
     [Q][P][3] (start, end, score) with their counts, saliency [Q][L] with the clip counts - against
     `pack_ground_truth(...)`: what `eval_epoch` gets from writing the submission rows and calling
-    `eval_submission` (inference.py:355-385), without the predictions leaving the GPU.  round_4dp applies the
-    submission's 4-decimal rounding of scores and saliency (inference.py:286-290, 318-320) first."""
+    `eval_submission` (inference.py:355-385), without the predictions leaving the GPU.  `windows` are the
+    POST-PROCESSED rows (FvtgResult.windows / nms_windows): their start / end already went through the compose
+    rounding and round_to_multiple_clip_lengths and are used as they are (postprocessing.py:31-33 re-rounds the
+    score only - re-rounding start / end would move them when clip_length is not a 4-decimal number, e.g.
+    0.166666 for Charades-VGG); round_4dp applies the submission's 4-decimal rounding to the scores and the
+    saliency (inference.py:286-290, 318-320)."""
     w = windows.to(torch.float64)
     sal = None if saliency is None else saliency.to(torch.float64)
     if round_4dp:
-        w = torch.round(w * 1e4) / 1e4
+        w = torch.cat([w[..., :2], torch.round(w[..., 2:3] * 1e4) / 1e4], -1)
         if sal is not None:
             sal = torch.round(sal * 1e4) / 1e4
     mr, hl = eval_arrays(w, counts, gt["gt_win"], gt["gt_cnt"], sal, sal_len,

@@ -187,6 +187,9 @@ class FlashVTGB200(torch.nn.Module):
         # generator.py:60: the reference asserts each level fits the anchor buffer
         if Lv > cfg.buffer_size:
             raise ValueError(f"Lv {Lv} exceeds the anchor buffer ({cfg.buffer_size} points, generator.py:60)")
+        if Lv > 1024:
+            raise ValueError(f"Lv {Lv}: the sm_100a kernels support at most 1024 clips per video (the reference "
+                             f"accepts up to buffer_size = {cfg.buffer_size} for this preset)")
         if duration is None:
             duration = vid_len.to(torch.float32) * cfg.clip_length
         duration = duration.to(device=dev, dtype=torch.float32).contiguous()

@@ -19,9 +19,9 @@ from helpers import GOLDEN, c_nms_f32, c_nms_hull, denan, load_forward_index, ma
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-2
-TOL_LOGIT = 3e-2
+TOL_LOGIT = 2.5e-2   # pre-sigmoid logits: profiles/r02_logit_error.md (worst measured 1.9e-2; the bf16-emulating oracle alone is at 2.2e-2)
 TOL_EMU = 4e-3
-TOL_EMU_LOGIT = 2.5e-2
+TOL_EMU_LOGIT = 2e-2
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
