@@ -157,6 +157,7 @@ DBG_SIGNATURES = {
     "fvtg_dbg_stream_probe": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "fvtg_dbg_inproj": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "fvtg_dbg_mufu_probe": (i32, [i32, i32, vp, vp]),
+    "fvtg_dbg_store_probe": (i32, [i32, i32, i32, vp, vp, vp]),
 }
 DBG_LIB_PATH = PKG_DIR / "libflashvtg_b200_dbg.so"
 

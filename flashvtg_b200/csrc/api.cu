@@ -56,6 +56,7 @@ struct Ws {
   // fusion
   bf16 *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
   float *Xf, *Yf, *pos_v, *pos_d, *tsum, *sal_scratch;
+  float2 *Xstat, *Ystat;   // per-row (rstd, -mean * rstd) of a layer kernel's deferred LayerNorm-2 (layer.cu)
   // pyramid + heads
   bf16 *chain0, *chainA[FVTG_MAX_LEVELS], *chainB[FVTG_MAX_LEVELS], *H1, *H2, *hA, *hB, *mA, *mB;
   // per-chunk head logits when the caller does not want them
@@ -77,6 +78,8 @@ static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws*
   t.Kc = k.take<bf16>(Rs * 256);
   t.Yf = k.take<float>(round_up_sz(Rv, 128) * 256);   // tile-blocked
   t.Yb = k.take<bf16>(Rv * 256);
+  t.Xstat = k.take<float2>(round_up_sz(Rs, 128));
+  t.Ystat = k.take<float2>(round_up_sz(Rv, 128));
   t.YPb = k.take<bf16>(Rv * 256);
   t.pos_v = k.take<float>(round_up_sz(Rv, 128) * 256);  // tile-blocked
   t.pos_d = k.take<float>(S * 256);
@@ -148,9 +151,18 @@ static int check_cfg(const FvtgCfg* c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static LayerArgs layer_args(const FvtgEncLayer& L, int rows, int mode, float* yf) {
+// prev: the layer kernel that produced yf and deferred its LayerNorm-2 to this one (null: yf is final);
+// stat: the stream's statistics buffer; defer: the next reader of yf is another layer kernel, which normalises.
+static LayerArgs layer_args(const FvtgEncLayer& L, int rows, int mode, float* yf, const FvtgEncLayer* prev,
+                            float2* stat, bool defer) {
   LayerArgs a;
   memset(&a, 0, sizeof(a));
+  if (prev) {
+    a.stats_in = stat;
+    a.pg = prev->norm2.g;
+    a.pbe = prev->norm2.b;
+  }
+  a.stats_out = defer ? stat : nullptr;
   a.M = rows;
   a.mode = mode;
   a.prelu = L.prelu;
@@ -169,7 +181,8 @@ static LayerArgs layer_args(const FvtgEncLayer& L, int rows, int mode, float* yf
 // out_b / out_pb: bf16(x) and bf16(x + pos) for the next layer's V and Q/K projections.
 static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, int Lseq, float* xf,
                     const bf16* xb, const bf16* xpb, bf16* out_b, bf16* out_pb, const float* pos,
-                    int pos_mod, int pos_rowlim, const int* klen_src, int kbase, int pos_cmp_L = 0) {
+                    int pos_mod, int pos_rowlim, const int* klen_src, int kbase, const FvtgEncLayer* prev,
+                    float2* stat, bool defer, int pos_cmp_L = 0) {
   const int rows = B * Lseq;
   {  // Q,K from x+pos ; V from x  (in_proj rows 0:512 / 512:768)
     GemmArgs g = gemm_args(rows, 768, 256, 256);
@@ -192,7 +205,7 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
     a.trace = dbg_trace();
     FVTG_TRY(launch_attention(st, a));
   }
-  LayerArgs a = layer_args(L, rows, LAYER_SA, xf);
+  LayerArgs a = layer_args(L, rows, LAYER_SA, xf, prev, stat, defer);
   a.out_b = out_b;
   a.out_pb = out_pb;
   a.pos = pos;
@@ -206,7 +219,8 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
 // One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396):
 // attention over the constant [dummies ‖ text] keys, then the fused layer kernel.
 static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, const Ws& w, int B,
-                     int Lv, int S, const int* tlen, bool want_b, int layer, int pos_cmp_L) {
+                     int Lv, int S, const int* tlen, bool want_b, int layer, int pos_cmp_L,
+                     const FvtgEncLayer* prev, bool defer) {
   const int rows = B * Lv;
   {
     AttnArgs a;
@@ -221,7 +235,7 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
     a.trace = dbg_trace();
     FVTG_TRY(launch_attention(st, a));
   }
-  LayerArgs a = layer_args(L, rows, LAYER_T2V, w.Yf);
+  LayerArgs a = layer_args(L, rows, LAYER_T2V, w.Yf, prev, w.Ystat, defer);
   a.out_b = want_b ? w.Yb : nullptr;
   a.out_pb = w.YPb;
   a.pos = w.pos_v;
@@ -273,19 +287,25 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
     e.pos_cmp_L = pos_cmp_L;
     FVTG_TRY(in_proj(st, W.vid, w, vid, B * Lv, c.v_dim, c.v_dim_pad, e));
   }
+  // Layer kernels of one stream hand their LayerNorm-2 to the next one (layer.cu): only the last kernel of a
+  // stream, whose fp32 output other kernels read, writes normalised rows.
   for (int i = 0; i < c.dummy_layers; ++i) {
     // the last dummy layer writes bf16(dummy + dummy_pos) straight into the key rows of Kc
     const bool last = i == c.dummy_layers - 1;
     FVTG_TRY(sa_layer(st, W.dummy[i], w, B, S, w.Xf, w.Xb, w.XPb, last ? nullptr : w.Xb,
-                      last ? w.Kc : w.XPb, w.pos_d, S, last ? nd : 0, tlen, nd));
+                      last ? w.Kc : w.XPb, w.pos_d, S, last ? nd : 0, tlen, nd,
+                      i > 0 ? &W.dummy[i - 1] : nullptr, w.Xstat, !last));
   }
   if (dummy_tokens) FVTG_TRY(launch_unblock(st, w.Xf, dummy_tokens, B, S, nd));
+  const int n_video_layers = c.t2v_layers + c.enc_layers;
   for (int i = 0; i < c.t2v_layers; ++i)
-    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1, i, pos_cmp_L));
+    FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1, i, pos_cmp_L,
+                       i > 0 ? &W.t2v[i - 1] : nullptr, i < n_video_layers - 1));
   for (int i = 0; i < c.enc_layers; ++i) {
     const bool last = i == c.enc_layers - 1;
+    const FvtgEncLayer* prev = i > 0 ? &W.enc[i - 1] : (c.t2v_layers > 0 ? &W.t2v[c.t2v_layers - 1] : nullptr);
     FVTG_TRY(sa_layer(st, W.enc[i], w, B, Lv, w.Yf, w.Yb, w.YPb, last ? nullptr : w.Yb,
-                      last ? nullptr : w.YPb, w.pos_v, 0, 0, vlen, 0, pos_cmp_L));
+                      last ? nullptr : w.YPb, w.pos_v, 0, 0, vlen, 0, prev, w.Ystat, !last, pos_cmp_L));
   }
   FVTG_TRY(launch_saliency(st, w.Yf, vlen, W.sal_w1, W.sal_b1, W.sal_w2t, W.sal_b2, w.tsum,
                            c.t2v_layers, w.sal_scratch, saliency, t2v, B, Lv));

@@ -31,6 +31,12 @@ struct LayerArgs {
   float prelu;
   const float *bo, *g1, *be1, *b1, *b2, *g2, *be2;
   float* yf;         // fp32 residual stream, tile-blocked (blk_off), read then overwritten
+  // deferred LayerNorm-2 across kernels: a layer whose only fp32 consumer is the next layer kernel leaves the RAW
+  // sums in yf plus (rstd, -mean * rstd) per row in stats_out, and the consumer applies ((raw * rstd - mean * rstd)
+  // * pg + pbe) while it reads its residual (stats_in / pg / pbe = the producer's stats_out / norm2 gamma / beta).
+  const float2* stats_in;   // null: yf holds final values
+  const float *pg, *pbe;
+  float2* stats_out;        // null: this kernel writes y itself
   bf16* out_b;       // bf16(y) [M][256] row-major or null
   bf16* out_pb;      // bf16(y + pos) [M][256] or null
   const float* pos;  // pos_mod == 0: tile-blocked per-row table ; > 0: row-major [pos_mod][256] ; null = 0
@@ -38,6 +44,7 @@ struct LayerArgs {
   int pos_cmp_L;     // > 0: pos is the compact table [64][pos_cmp_L][4], row -> row % pos_cmp_L (uniform-length chunk)
   int pos_rowlim;    // > 0: out_pb only for rows with row % pos_mod < pos_rowlim
   long long* trace;  // debug: per-phase clock64 stamps of CTA 0 (fvtg_dbg_set_trace), null in production
+  int trace_cta;     // debug: the CTA whose stamps are recorded (env FVTG_TRACE_CTA)
   int stagger_ns;    // start-up delay step: cluster c sleeps (c % 8) * stagger_ns before its first tile
   int dbg;           // debug (env FVTG_LAYER_DBG): bit 0 skip residual loads, bit 1 skip pos loads, bit 2 skip global stores
   int tile_rows;     // rows a tile advances by (<= 128, multiple of 8; set by launch_layer): the MMAs always run

@@ -25,7 +25,11 @@
 //         EPI2: h = PReLU(H[p&1] + b1[p]) -> bf16 pairs -> tcgen05.st back into the SAME columns
 //               (each thread overwrites only columns it alone has read)
 //         MMA : Z += h . W2[:, p]^T                      8 x (128 x 256 x 16), A operand from TMEM
-//   EPI3: y = LayerNorm2(Z + b2) -> fp32 residual stream, bf16(y), bf16(y + pos)
+//   EPI3: LayerNorm2(Z + b2) in two TMEM passes.  Pass 1: row statistics + the fp32 row of the residual stream -
+//         the RAW sums plus (rstd, -mean * rstd) per row when the next reader is another layer kernel (it
+//         normalises inside its EPI1: stats_in / pg / pbe), so the statistics pass carries half of the tile's
+//         stores.  Pass 2: bf16(y), bf16(y + pos) as paired 64-byte row segments (and y itself for the last layer
+//         of a stream).  The phase is bound by the SM's ~30 B/cycle store port (tools/probe_store.py).
 //
 // 20 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..19 epilogue (four threads per row: TMEM lane quadrant = warp % 4, column
 // quarter = (warp - 4) / 4).
@@ -50,7 +54,7 @@ static_assert(LK_SMEM_BYTES <= 232448, "layer kernel shared memory over the 227 
 // trace slots: [role 0 MMA / 1 epilogue][tile it < 8][event < 32]
 #define LK_TRACE(role, ev)                                                              \
   do {                                                                                  \
-    if (g.trace && blockIdx.x == 0 && it < 8)                                           \
+    if (g.trace && static_cast<int>(blockIdx.x) == g.trace_cta && it < 8)                                           \
       g.trace[((role) * 8 + it) * 32 + (ev)] = clock64();                               \
   } while (0)
 
@@ -97,14 +101,14 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 20);
   float2* s_stat = reinterpret_cast<float2*>(smem + LK_OFF_STAT);  // [2 phases][4 quarters][128]
   float* s_par = reinterpret_cast<float*>(smem + LK_OFF_PAR);
-  float* s_bo = s_par;
+  float* s_bo = s_par;            // bo (+ pbe of the producer's deferred LayerNorm-2)
   float* s_g1 = s_par + 256;
   float* s_be1 = s_par + 512;
   float* s_b1 = s_par + 768;
-  float* s_b2 = s_par + 1792;
+  float* s_pg = s_par + 1792;     // gamma of the producer's deferred LayerNorm-2 (1 when the residual is final)
   float* s_g2 = s_par + 2048;
   float* s_be2 = s_par + 2304;
-  float* s_be1z = s_par + 2560;   // be1 + b2: the SA-mode FFN residual LN1(z) enters Z with ff2's bias folded in
+  float* s_b2z = s_par + 2560;    // T2V: b2 ; SA: be1 + b2 (the FFN residual LN1(z) enters Z with ff2's bias folded in)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,16 +142,22 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < 256; i += LK_THREADS) {
-    s_bo[i] = g.bo[i];
+    s_bo[i] = g.bo[i] + (g.stats_in ? g.pbe[i] : 0.f);
+    s_pg[i] = g.stats_in ? g.pg[i] : 1.f;
     s_g1[i] = g.g1[i];
     s_be1[i] = g.be1[i];
-    s_b2[i] = g.b2[i];
     s_g2[i] = g.g2[i];
     s_be2[i] = g.be2[i];
-    s_be1z[i] = g.be1[i] + g.b2[i];
+    s_b2z[i] = g.mode == LAYER_SA ? g.be1[i] + g.b2[i] : g.b2[i];
   }
   for (int i = threadIdx.x; i < 1024; i += LK_THREADS) s_b1[i] = g.b1[i];
   pdl_wait();   // everything above touched only constants / on-chip state
+  if (g.trace && static_cast<int>(blockIdx.x) == g.trace_cta && threadIdx.x == 0) {
+    long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g.trace[512] = ns;
+    g.trace[513] = clock64();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -307,8 +317,35 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int qt = ew >> 2;  // column quarter
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t u[32];
+    const bool tr = (warp == 4 && lane == 0);
+    uint32_t u[16];
     int it = 0;
+
+    // The residual stream may arrive un-normalised: when the producing layer kernel deferred its LayerNorm-2 to
+    // its consumer (stats_in != null), yf holds the raw sums and (rstd, -mean * rstd) per row; x = (raw * rstd
+    // - mean * rstd) * pg + pbe is applied here (pbe is folded into s_bo).  Otherwise (1, 0) with pg = 1.
+    ulonglong2 rr[4];
+    float r_rs = 1.f, r_nm = 0.f;
+    // first residual chunk (16 columns) of a tile: it depends on no MMA, so it is fetched a phase early - before
+    // the first tile, and for every later tile before the previous tile's drain puts 128 KB of stores in front of
+    // it; the other three chunks follow one chunk ahead of their use inside epilogue 1
+    auto load_res0 = [&](int t) {
+      const int rw_ = t * g.tile_rows + r;
+      const bool ok = t < ntiles && r < g.tile_rows && rw_ < g.M && !(g.dbg & 1);
+      const float* src = g.yf + static_cast<size_t>(rw_ >> 7) * (128 * 256) + (rw_ & 127) * 4 +
+                         static_cast<size_t>(qt) * (16 * 512);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rr[i] = ok ? ld_p4(src + i * 512) : make_ulonglong2(0ull, 0ull);
+      r_rs = 1.f;
+      r_nm = 0.f;
+      if (ok && g.stats_in) {
+        const float2 st = g.stats_in[rw_];
+        r_rs = st.x;
+        r_nm = st.y;
+      }
+    };
+
+    load_res0(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int row = tile * g.tile_rows + r;
       const bool inb = r < g.tile_rows && row < g.M;
@@ -316,45 +353,41 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // fp32 residual stream, blocked by 128 rows: [row/128][col/4][row%128][4]
       const size_t blk = static_cast<size_t>(row >> 7) * (128 * 256) + (row & 127) * 4;
       float* yblk = g.yf + blk;
-      const bool tr = (warp == 4 && lane == 0);
 
       // ---- epilogue 1: z = H + bo + x ; LayerNorm1 -> sA ; FFN residual into Z -----------------
       // (packed fp32 pairs throughout: add.f32x2 / fma.rn.f32x2 halve the FP instruction count)
       if (tr) LK_TRACE(1, 0);
-      ulonglong2 rr[8];
       const float* ysrc = yblk + static_cast<size_t>(qt) * (16 * 512);   // this thread's column quarter
-      {  // the first residual chunk does not depend on the MMA: fetch it before waiting
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rr[i] = ldres ? ld_p4(ysrc + i * 512) : make_ulonglong2(0ull, 0ull);
-      }
       mbar_wait(z1_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 1);
       float shift = 0.f;
       uint64_t nsh2 = 0ull, a1 = 0ull, a2 = 0ull;
+      {
+        const uint64_t rrs2 = f2_pack(r_rs, r_rs), rnm2 = f2_pack(r_nm, r_nm);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = qt * 64 + c * 32;
-        tmem_ld32(tmem_h + lane_addr + c0, u);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {   // 16 columns at a time: half the registers of a 32-column pass
+          const int c0 = qt * 64 + c * 16;
+          tmem_ld16(tmem_h + lane_addr + c0, u);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const ulonglong2 b = ld_p4(s_bo + c0 + 4 * i);
-          unpk2(f2_add(f2_add(pk2(u, 2 * i), b.x), rr[i].x), u, 2 * i);
-          unpk2(f2_add(f2_add(pk2(u, 2 * i + 1), b.y), rr[i].y), u, 2 * i + 1);
-        }
-        if (c == 0) {
+          for (int i = 0; i < 4; ++i) {
+            const ulonglong2 b = ld_p4(s_bo + c0 + 4 * i), pg4 = ld_p4(s_pg + c0 + 4 * i);
+            unpk2(f2_add(pk2(u, 2 * i), f2_fma(f2_fma(rr[i].x, rrs2, rnm2), pg4.x, b.x)), u, 2 * i);
+            unpk2(f2_add(pk2(u, 2 * i + 1), f2_fma(f2_fma(rr[i].y, rrs2, rnm2), pg4.y, b.y)), u, 2 * i + 1);
+            if (c < 3) rr[i] = ldres ? ld_p4(ysrc + ((c + 1) * 4 + i) * 512) : make_ulonglong2(0ull, 0ull);
+          }
+          if (c == 0) {
+            shift = __uint_as_float(u[0]);
+            nsh2 = f2_pack(-shift, -shift);
+          }
+          tmem_st16(tmem + lane_addr + c0, u);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rr[i] = ldres ? ld_p4(ysrc + (8 + i) * 512) : make_ulonglong2(0ull, 0ull);
-          shift = __uint_as_float(u[0]);
-          nsh2 = f2_pack(-shift, -shift);
-        }
-        tmem_st32(tmem + lane_addr + c0, u);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint64_t d = f2_add(pk2(u, j), nsh2);
-          a1 = f2_add(a1, d);
-          a2 = f2_fma(d, d, a2);
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t d = f2_add(pk2(u, j), nsh2);
+            a1 = f2_add(a1, d);
+            a2 = f2_fma(d, d, a2);
+          }
         }
       }
       {
@@ -378,34 +411,33 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       {
         const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
+        uint8_t* unit = sA + qt * LK_UNIT;   // this thread's column quarter == one 64-column SWIZZLE_128B unit
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int c0 = qt * 64 + c * 32;
-          tmem_ld32(tmem + lane_addr + c0, u);
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = qt * 64 + c * 16;
+          tmem_ld16(tmem + lane_addr + c0, u);
           tmem_ld_wait();
-          uint32_t w[16];
+          uint32_t w[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const ulonglong2 gm = ld_p4(s_g1 + c0 + 4 * i), bt = ld_p4(s_be1 + c0 + 4 * i);
             const uint64_t t0 = f2_fma(pk2(u, 2 * i), rs2, nm2), t1 = f2_fma(pk2(u, 2 * i + 1), rs2, nm2);
             w[2 * i] = bf16x2_of(f2_fma(t0, gm.x, bt.x));
             w[2 * i + 1] = bf16x2_of(f2_fma(t1, gm.y, bt.y));
-            if (g.mode == LAYER_SA) {   // the FFN residual is LN1(z): Z <- LN1(z) + b2
-              const ulonglong2 bz = ld_p4(s_be1z + c0 + 4 * i);
+            // s_b2z = b2 (T2V: the FFN residual is the pre-LN1 sum z) or be1 + b2 (SA: it is LN1(z))
+            const ulonglong2 bz = ld_p4(s_b2z + c0 + 4 * i);
+            if (g.mode == LAYER_SA) {
               unpk2(f2_fma(t0, gm.x, bz.x), u, 2 * i);
               unpk2(f2_fma(t1, gm.y, bz.y), u, 2 * i + 1);
-            } else {                    // ... the pre-LN1 sum: Z <- z + b2
-              const ulonglong2 bz = ld_p4(s_b2 + c0 + 4 * i);
+            } else {
               unpk2(f2_add(pk2(u, 2 * i), bz.x), u, 2 * i);
               unpk2(f2_add(pk2(u, 2 * i + 1), bz.y), u, 2 * i + 1);
             }
           }
-          tmem_st32(tmem + lane_addr + c0, u);
-          uint8_t* unit = sA + (c0 >> 6) * LK_UNIT;
-          const int cf = (c0 & 63) >> 3;
+          tmem_st16(tmem + lane_addr + c0, u);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(unit + sw128_off(r, cf + q4)) =
+          for (int q4 = 0; q4 < 2; ++q4)
+            *reinterpret_cast<uint4*>(unit + sw128_off(r, c * 2 + q4)) =
                 make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
         }
       }
@@ -416,7 +448,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(ln_ready);
       if (tr) LK_TRACE(1, 3);
 
-      // ---- epilogue 2 (x8): hidden piece = PReLU(H[buf] + b1) -> bf16 pairs back into H[buf] --
+      // ---- epilogue 2 (x8): hidden piece = PReLU(H[buf] + b1) -> bf16 pairs back into H[buf] (two 16-column
+      //      halves) ----------------------------------------------------------------------------------------
+      const uint64_t al2 = f2_pack(g.prelu, g.prelu);
+      const bool prelu_max = g.prelu >= 0.f && g.prelu <= 1.f;   // PReLU(x) = max(x, a x): no compare / select
 #pragma unroll 1
       for (int p = 0; p < 8; ++p) {
         const int buf = p & 1;
@@ -425,41 +460,36 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         if (tr) LK_TRACE(1, 4 + 2 * p);
         const uint32_t ha = tmem_h + lane_addr + buf * 128 + qt * 32;
-        tmem_ld32(ha, u);
-        tmem_ld_wait();
-        const float* bb = s_b1 + p * 128 + qt * 32;
-        uint32_t hp[16];
-        const uint64_t al2 = f2_pack(g.prelu, g.prelu);
-        if (g.prelu >= 0.f && g.prelu <= 1.f) {   // PReLU(x) = max(x, a x) for 0 <= a <= 1: no compare / select
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+        for (int hh = 0; hh < 2; ++hh) {
+          tmem_ld16(ha + hh * 16, u);
+          tmem_ld_wait();
+          const float* bb = s_b1 + p * 128 + qt * 32 + hh * 16;
+          uint32_t hp[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
             const ulonglong2 b = ld_p4(bb + 4 * i);
             const uint64_t x0 = f2_add(pk2(u, 2 * i), b.x), x1 = f2_add(pk2(u, 2 * i + 1), b.y);
-            float a0, a1, a2, a3, m0, m1, m2, m3;
+            float a0, a1, a2, a3;
             f2_unpack(x0, a0, a1);
             f2_unpack(x1, a2, a3);
-            f2_unpack(f2_mul(x0, al2), m0, m1);
-            f2_unpack(f2_mul(x1, al2), m2, m3);
-            hp[2 * i + 0] = pack_bf16(fmaxf(a0, m0), fmaxf(a1, m1));
-            hp[2 * i + 1] = pack_bf16(fmaxf(a2, m2), fmaxf(a3, m3));
+            if (prelu_max) {
+              float m0, m1, m2, m3;
+              f2_unpack(f2_mul(x0, al2), m0, m1);
+              f2_unpack(f2_mul(x1, al2), m2, m3);
+              hp[2 * i + 0] = pack_bf16(fmaxf(a0, m0), fmaxf(a1, m1));
+              hp[2 * i + 1] = pack_bf16(fmaxf(a2, m2), fmaxf(a3, m3));
+            } else {
+              a0 = a0 > 0.f ? a0 : g.prelu * a0;
+              a1 = a1 > 0.f ? a1 : g.prelu * a1;
+              a2 = a2 > 0.f ? a2 : g.prelu * a2;
+              a3 = a3 > 0.f ? a3 : g.prelu * a3;
+              hp[2 * i + 0] = pack_bf16(a0, a1);
+              hp[2 * i + 1] = pack_bf16(a2, a3);
+            }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = ld_f4(bb + 4 * i);
-            float x0 = __uint_as_float(u[4 * i + 0]) + b.x;
-            float x1 = __uint_as_float(u[4 * i + 1]) + b.y;
-            float x2 = __uint_as_float(u[4 * i + 2]) + b.z;
-            float x3 = __uint_as_float(u[4 * i + 3]) + b.w;
-            x0 = x0 > 0.f ? x0 : g.prelu * x0;
-            x1 = x1 > 0.f ? x1 : g.prelu * x1;
-            x2 = x2 > 0.f ? x2 : g.prelu * x2;
-            x3 = x3 > 0.f ? x3 : g.prelu * x3;
-            hp[2 * i + 0] = pack_bf16(x0, x1);
-            hp[2 * i + 1] = pack_bf16(x2, x3);
-          }
+          tmem_st8(ha + hh * 8, hp);   // packed pairs land in columns this thread alone has already read
         }
-        tmem_st16(ha, hp);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -467,28 +497,39 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (tr) LK_TRACE(1, 5 + 2 * p);
       }
 
-      // ---- final epilogue: y = LayerNorm2(Z) (b2 is already in Z) -> residual stream / bf16 operands --
+      // ---- final epilogue: LayerNorm2(Z) (b2 is already in Z).  An SM stores only ~30 B/cycle (tools/probe_store.py),
+      //      so the 192-256 KB a tile writes bound this phase, not arithmetic: the statistics pass, which used to
+      //      store nothing, now carries the fp32 row (the RAW sums plus (rstd, -mean * rstd) per row when the next
+      //      reader is another layer kernel, which normalises while it reads its residual), and the second pass only
+      //      the bf16 operands, as paired 64-byte row segments (full store-port rate instead of half) ------------
       int prow = row;
       if (g.pos_mod > 0) prow = row % g.pos_mod;
-      const bool st_pos = g.out_pb && inb && (g.pos_rowlim <= 0 || prow < g.pos_rowlim);
-      const bool ld_pos = st_pos && g.pos && !(g.dbg & 2);
       const bool st_ok = inb && !(g.dbg & 4);
-      const bool st_pb = st_pos && !(g.dbg & 4);
+      const bool st_pb = g.out_pb && st_ok && (g.pos_rowlim <= 0 || prow < g.pos_rowlim);
+      const bool ld_pos = g.out_pb && g.pos && inb && (g.pos_rowlim <= 0 || prow < g.pos_rowlim) && !(g.dbg & 2);
+      load_res0(tile + static_cast<int>(gridDim.x));
       mbar_wait(z2_full, it & 1);
       tc_fence_after();
       if (tr) LK_TRACE(1, 20);
       a1 = 0ull;
       a2 = 0ull;
+      float* ydst = yblk + static_cast<size_t>(qt) * (16 * 512);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tmem_ld32(tmem + lane_addr + qt * 64 + c * 32, u);
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld16(tmem + lane_addr + qt * 64 + c * 16, u);
         tmem_ld_wait();
         if (c == 0) {
           shift = __uint_as_float(u[0]);
           nsh2 = f2_pack(-shift, -shift);
         }
+        if (st_ok && g.stats_out) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(ydst + (c * 4 + i) * 512) =
+                make_uint4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
           const uint64_t d = f2_add(pk2(u, j), nsh2);
           a1 = f2_add(a1, d);
           a2 = f2_fma(d, d, a2);
@@ -510,9 +551,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float m2 = a0.y + a1.y + a2.y + a3.y + 64.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
         rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
       }
-      {
+      if (g.stats_out && qt == 0 && st_ok) g.stats_out[row] = make_float2(rstd, -mean * rstd);
+      if (g.out_b || g.out_pb || !g.stats_out) {
         const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
-        float* ydst = yblk + static_cast<size_t>(qt) * (16 * 512);
         const float* psrc = nullptr;   // this lane's position row, first column of its quarter
         size_t pstep = 0;              // floats between consecutive 4-column groups
         if (ld_pos) {
@@ -523,31 +564,37 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else { psrc = g.pos + blk + static_cast<size_t>(qt) * (16 * 512); pstep = 512; }
         }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(tmem + lane_addr + qt * 64 + c * 32, u);
+        for (int c = 0; c < 2; ++c) {   // 32 columns: 64 bytes of each bf16 output row
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_addr + qt * 64 + c * 32, v);
           tmem_ld_wait();
+          const int c0 = qt * 64 + c * 32;
+          uint32_t w[16];
 #pragma unroll
-          for (int h16 = 0; h16 < 2; ++h16) {   // 16 columns: one 32-byte sector of each bf16 output row
-            const int c0 = qt * 64 + c * 32 + h16 * 16;
-            uint32_t w[8], wp[8];
+          for (int i = 0; i < 8; ++i) {
+            const ulonglong2 gm = ld_p4(s_g2 + c0 + 4 * i), bt = ld_p4(s_be2 + c0 + 4 * i);
+            const uint64_t y0 = f2_fma(f2_fma(pk2(v, 2 * i), rs2, nm2), gm.x, bt.x);
+            const uint64_t y1 = f2_fma(f2_fma(pk2(v, 2 * i + 1), rs2, nm2), gm.y, bt.y);
+            unpk2(y0, v, 2 * i);
+            unpk2(y1, v, 2 * i + 1);
+            w[2 * i] = bf16x2_of(y0);
+            w[2 * i + 1] = bf16x2_of(y1);
+          }
+          if (!g.stats_out && st_ok) {   // no consumer kernel will normalise: y itself goes to the residual buffer
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int g4 = c * 8 + h16 * 4 + i;   // 4-column group within the quarter
-              const ulonglong2 gm = ld_p4(s_g2 + c0 + 4 * i), bt = ld_p4(s_be2 + c0 + 4 * i);
-              ulonglong2 y;
-              y.x = f2_fma(f2_fma(pk2(u, h16 * 8 + 2 * i), rs2, nm2), gm.x, bt.x);
-              y.y = f2_fma(f2_fma(pk2(u, h16 * 8 + 2 * i + 1), rs2, nm2), gm.y, bt.y);
-              if (st_ok) *reinterpret_cast<ulonglong2*>(ydst + g4 * 512) = y;
-              w[2 * i] = bf16x2_of(y.x);
-              w[2 * i + 1] = bf16x2_of(y.y);
-              if (g.out_pb) {
-                const ulonglong2 pv = psrc ? ld_p4(psrc + g4 * pstep) : make_ulonglong2(0ull, 0ull);
-                wp[2 * i] = bf16x2_of(f2_add(y.x, pv.x));
-                wp[2 * i + 1] = bf16x2_of(f2_add(y.y, pv.y));
-              }
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<uint4*>(ydst + (c * 8 + i) * 512) =
+                  make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (g.out_b) st_global_bf16x32_paired_w(g.out_b + static_cast<size_t>(row) * 256 + c0, 256, st_ok, w);
+          if (g.out_pb) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const ulonglong2 pv = psrc ? ld_p4(psrc + (c * 8 + i) * pstep) : make_ulonglong2(0ull, 0ull);
+              w[2 * i] = bf16x2_of(f2_add(pk2(v, 2 * i), pv.x));
+              w[2 * i + 1] = bf16x2_of(f2_add(pk2(v, 2 * i + 1), pv.y));
             }
-            if (g.out_b && st_ok) st_global_v8(g.out_b + static_cast<size_t>(row) * 256 + c0, w);
-            if (g.out_pb && st_pb) st_global_v8(g.out_pb + static_cast<size_t>(row) * 256 + c0, wp);
+            st_global_bf16x32_paired_w(g.out_pb + static_cast<size_t>(row) * 256 + c0, 256, st_pb, w);
           }
         }
       }
@@ -560,6 +607,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
+  if (g.trace && static_cast<int>(blockIdx.x) == g.trace_cta && threadIdx.x == 0) {
+    long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g.trace[514] = ns;
+    g.trace[515] = clock64();
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -599,6 +652,8 @@ int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w
   {
     const char* d = getenv("FVTG_LAYER_DBG");
     a2.dbg = d ? atoi(d) : 0;
+    const char* tc = getenv("FVTG_TRACE_CTA");
+    a2.trace_cta = tc ? atoi(tc) : 0;
     const char* sg = getenv("FVTG_LAYER_STAGGER_NS");
     a2.stagger_ns = sg ? atoi(sg) : 3000;
     // debug: trace only the k-th layer launch of each forward (FVTG_TRACE_LAYER_IDX, 11 launches per forward at QVH)

@@ -481,4 +481,75 @@ extern "C" int32_t fvtg_dbg_mufu_probe(int32_t warps, int32_t iters, float* out,
   return FVTG_OK;
 }
 
+// fvtg_dbg_store_probe: per-SM global store / load throughput with the layer kernel's epilogue access shapes.
+// 512 threads; per repetition a CTA touches one 128-row tile: mode 0 = fp32 tile-blocked stores (16 x 16 B per
+// thread, a warp writes 512 contiguous bytes), 1 = bf16 row-major rows (8 x 32 B per thread at a 512 B row pitch,
+// two outputs), 2 = both (the LayerNorm-2 mix, 256 KB), 3 = fp32 tile-blocked loads (the residual read).
+namespace fvtg {
+__global__ void __launch_bounds__(512, 1)
+store_probe_kernel(int mode, int reps, uint8_t* buf, long long* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, qt = warp >> 2, r = q * 32 + lane;
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int rep = 0; rep < reps; ++rep) {
+    uint8_t* tile = buf + (static_cast<size_t>(rep) * gridDim.x + blockIdx.x) * (256u << 10);
+    float* yf = reinterpret_cast<float*>(tile) + qt * (16 * 512) + r * 4;
+    if (mode == 0 || mode == 2) {
+#pragma unroll
+      for (int g4 = 0; g4 < 16; ++g4)
+        *reinterpret_cast<float4*>(yf + g4 * 512) = make_float4(rep, g4, r, qt);
+    }
+    if (mode == 1 || mode == 2) {
+      uint8_t* b0 = tile + (128u << 10) + static_cast<size_t>(r) * 512 + qt * 128;
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[8] = {1u, 2u, 3u, 4u, 5u, 6u, 7u, static_cast<uint32_t>(rep)};
+          st_global_v8(reinterpret_cast<bf16*>(b0 + o * (64u << 10) + j * 32), w);
+        }
+    }
+    if (mode >= 4) {   // TMA bulk stores from shared memory: 4 = 4 x 32 KB, 5 = 16 x 8 KB, 6 = 64 x 2 KB per tile
+      extern __shared__ __align__(1024) uint8_t sm[];
+      const int n = mode == 4 ? 4 : (mode == 5 ? 16 : 64);
+      const uint32_t sz = (128u << 10) / n;
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < n; ++i)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tile + i * sz),
+                       "r"(smem_u32(sm) + (i * sz) % 32768u), "r"(sz) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (mode == 3) {
+#pragma unroll
+      for (int g4 = 0; g4 < 16; ++g4) {
+        const float4 v = *reinterpret_cast<const float4*>(yf + g4 * 512);
+        acc += v.x + v.y + v.z + v.w;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  if (mode >= 4 && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  __syncthreads();
+  const long long t2 = clock64();
+  if (threadIdx.x == 0) {
+    out[blockIdx.x * 2] = t1 - t0;
+    out[blockIdx.x * 2 + 1] = t2 - t0;
+  }
+  if (acc == 123.456f) out[0] = 0;
+}
+}  // namespace fvtg
+extern "C" int32_t fvtg_dbg_store_probe(int32_t mode, int32_t reps, int32_t grid, void* buf, void* out_cycles,
+                                        void* stream) {
+  using namespace fvtg;
+  if (mode < 0 || mode > 6 || reps < 1 || grid < 1) return fail(FVTG_EINVAL, "store probe: bad arguments");
+  store_probe_kernel<<<grid, 512, 32768, static_cast<cudaStream_t>(stream)>>>(mode, reps, static_cast<uint8_t*>(buf),
+                                                                         static_cast<long long*>(out_cycles));
+  FVTG_LAUNCH_CHECK("store_probe_kernel");
+  return FVTG_OK;
+}
+
 #endif  // FVTG_DEBUG_HOOKS

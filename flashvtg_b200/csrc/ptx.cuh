@@ -370,6 +370,20 @@ __device__ __forceinline__ void st_global_bf16x32_paired(__nv_bfloat16* dst, int
   // second row: lane 0 received lane 1's columns 0..15, lane 1 holds its own 16..31
   if (ok1) st_global_v8(row0 + pitch, m ? w + 8 : rcv);
 }
+// the same with the 32 columns already packed as 16 bf16 pairs
+__device__ __forceinline__ void st_global_bf16x32_paired_w(__nv_bfloat16* dst, int pitch, bool ok,
+                                                           const uint32_t* w) {
+  const int lane = threadIdx.x & 31;
+  const int m = lane & 1;
+  uint32_t rcv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rcv[i] = __shfl_xor_sync(0xffffffffu, m ? w[i] : w[8 + i], 1);
+  const bool ok0 = __shfl_sync(0xffffffffu, ok, lane & ~1);
+  const bool ok1 = __shfl_sync(0xffffffffu, ok, lane | 1);
+  __nv_bfloat16* row0 = dst - m * pitch + m * 16;
+  if (ok0) st_global_v8(row0, m ? rcv : w);
+  if (ok1) st_global_v8(row0 + pitch, m ? w + 8 : rcv);
+}
 }  // namespace fvtg
 
 namespace fvtg {

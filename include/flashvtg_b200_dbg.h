@@ -35,6 +35,10 @@ int32_t fvtg_dbg_stream_probe(const float* x, int32_t rows, int32_t dim, int32_t
 /* out[0] = cycles per warp-wide ex2.approx.ftz.f32 with `warps` (1..32) warps per SM issuing 8 independent chains each,
  * out[1] = the same for fma.rn.f32 (the issue-rate reference). */
 int32_t fvtg_dbg_mufu_probe(int32_t warps, int32_t iters, float* out, void* stream);
+/* Per-SM global store / load rate with the layer kernel's epilogue access shapes: mode 0 fp32 tile-blocked stores,
+ * 1 bf16 row-major stores, 2 both (256 KB per tile), 3 fp32 tile-blocked loads; `grid` CTAs x `reps` tiles each over
+ * buf (>= grid * reps * 256 KB); out_cycles int64 [grid][2] = (issue loop, until the stores are performed). */
+int32_t fvtg_dbg_store_probe(int32_t mode, int32_t reps, int32_t grid, void* buf, void* out_cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,12 +33,17 @@ def main():
     m.infer(d["src_vid"], d["vid_len"], d["src_txt"], d["txt_len"])
     torch.cuda.synchronize()
     lib.fvtg_dbg_set_trace(None)
-    t = buf.cpu()[:512].view(2, 8, 32)
+    full = buf.cpu()
+    ns, cyc = int(full[514] - full[512]), int(full[515] - full[513])
+    if ns > 0:
+        print(f"CTA lifetime after griddepcontrol.wait: {ns / 1e3:.1f} us, {cyc} cycles -> {cyc / ns * 1e3:.0f} MHz")
+    t = full[:512].view(2, 8, 32)
     t0 = int(t[0, 0, 0])
     names_m = {0: "tile start", 1: "z_empty ok", 2: "a_full ok", 3: "out_proj issued", 4: "ln_ready ok",
                5: "ff1(0,1) issued", 22: "z2 commit"}
     names_e = {0: "tile start", 1: "z1_full ok", 2: "ep1 pass1 done", 3: "ep1 done (ln_ready)",
-               20: "z2_full ok", 21: "final pass1 done", 22: "final done (z_empty)"}
+               20: "z2_full ok", 21: "drain pass done", 22: "drain done (raw_ready)",
+               24: "NORM raw_ready ok", 25: "NORM half 0 done", 26: "NORM tile done"}
     for it in range(5):
         print(f"--- tile {it} (cycles since first tile start; 1 us ~ 1900 cycles at full clock)")
         ev = []
