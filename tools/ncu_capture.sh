@@ -27,5 +27,5 @@ a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16); b = torch.rand
 for _ in range(3): c = a @ b
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none -k regex:nvjet -s 2 -c 1 -f -o $O/prof_${TAG}_cublas_bf16_8192 python /tmp/cublas_cal.py > $O/ncu_${TAG}_cublas.log 2>&1
+ncu --set full --clock-control none -k regex:nvjet -s 1 -c 1 -f -o $O/prof_${TAG}_cublas_bf16_8192 python /tmp/cublas_cal.py > $O/ncu_${TAG}_cublas.log 2>&1
 ls -la $O/prof_${TAG}_*.ncu-rep
