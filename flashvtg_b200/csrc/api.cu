@@ -56,6 +56,7 @@ struct Ws {
   // fusion
   bf16 *tmp256, *Xb, *XPb, *Kc, *Yb, *YPb, *qkv, *att, *ffh;
   float *Xf, *Yf, *pos_v, *pos_d, *tsum, *sal_scratch;
+  int* Yflags;             // per-128-row-tile completion epochs of the video stream's layer kernels (attn.cu q_flags)
   float2 *Xstat, *Ystat;   // per-row (rstd, -mean * rstd) of a layer kernel's deferred LayerNorm-2 (layer.cu)
   // pyramid + heads
   bf16 *chain0, *chainA[FVTG_MAX_LEVELS], *chainB[FVTG_MAX_LEVELS], *H1, *H2, *hA, *hB, *mA, *mB;
@@ -80,6 +81,7 @@ static size_t carve(const FvtgCfg& c, int Bc, int Lv, int Lt, uint8_t* base, Ws*
   t.Yb = k.take<bf16>(Rv * 256);
   t.Xstat = k.take<float2>(round_up_sz(Rs, 128));
   t.Ystat = k.take<float2>(round_up_sz(Rv, 128));
+  t.Yflags = k.take<int>(Rv / 8 + 64);   // >= one flag per tile for tiles of >= 8 rows
   t.YPb = k.take<bf16>(Rv * 256);
   t.pos_v = k.take<float>(round_up_sz(Rv, 128) * 256);  // tile-blocked
   t.pos_d = k.take<float>(S * 256);
@@ -216,6 +218,12 @@ static int sa_layer(cudaStream_t st, const FvtgEncLayer& L, const Ws& w, int B, 
                       static_cast<const bf16*>(L.ff1.w), static_cast<const bf16*>(L.ff2.w), a);
 }
 
+// FVTG_TILE_HANDOFF=0 restores the grid-wide dependency between a T2V layer kernel and the next attention
+static bool tile_handoff() {
+  static const bool on = [] { const char* e = getenv("FVTG_TILE_HANDOFF"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
 // One adaptive cross-attention layer (transformer.py:334-369, crossattention.py:287-396):
 // attention over the constant [dummies ‖ text] keys, then the fused layer kernel.
 static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, const Ws& w, int B,
@@ -233,9 +241,18 @@ static int t2v_layer(cudaStream_t st, const FvtgCfg& c, const FvtgEncLayer& L, c
     a.klen_src = tlen; a.kbase = c.num_dummies; a.v_first = c.num_dummies;
     a.tsum = w.tsum + static_cast<size_t>(layer) * 8 * B * Lv;
     a.trace = dbg_trace();
+    if (layer > 0 && tile_handoff()) {   // q = YPb comes from the previous T2V layer kernel, tile by tile
+      a.q_flags = w.Yflags;
+      a.q_epoch = layer;
+      a.q_tile_rows = layer_tile_rows(rows);
+    }
     FVTG_TRY(launch_attention(st, a));
   }
   LayerArgs a = layer_args(L, rows, LAYER_T2V, w.Yf, prev, w.Ystat, defer);
+  if (tile_handoff()) {
+    a.tile_flags = w.Yflags;
+    a.flag_epoch = layer + 1;
+  }
   a.out_b = want_b ? w.Yb : nullptr;
   a.out_pb = w.YPb;
   a.pos = w.pos_v;
@@ -298,6 +315,10 @@ static int fusion_chunk(cudaStream_t st, const FvtgCfg& c, const FvtgWeights& W,
   }
   if (dummy_tokens) FVTG_TRY(launch_unblock(st, w.Xf, dummy_tokens, B, S, nd));
   const int n_video_layers = c.t2v_layers + c.enc_layers;
+  if (c.t2v_layers > 1 && tile_handoff()) {
+    FVTG_CUDA_OK(cudaMemsetAsync(w.Yflags, 0, sizeof(int) * (static_cast<size_t>(B) * Lv / 8 + 64), st));
+    count_launch(1);
+  }
   for (int i = 0; i < c.t2v_layers; ++i)
     FVTG_TRY(t2v_layer(st, c, W.t2v[i], w, B, Lv, S, tlen, i == c.t2v_layers - 1, i, pos_cmp_L,
                        i > 0 ? &W.t2v[i - 1] : nullptr, i < n_video_layers - 1));

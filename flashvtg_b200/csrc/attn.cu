@@ -44,7 +44,20 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   pdl_launch_dependents();
-  pdl_wait();
+  if (a.q_flags) {
+    // tile-granular dependency on the producing layer kernel (see AttnArgs::q_flags).  The spin is bounded: a
+    // protocol error shows up as a parity failure, never as a hung GPU.
+    if (tid == 0) {
+      const int t0 = (b * a.Lq) / a.q_tile_rows, t1 = (b * a.Lq + a.Lq - 1) / a.q_tile_rows;
+      for (int t = t0; t <= t1; ++t) {
+        int spins = 0;
+        while (ld_acquire_gpu(a.q_flags + t) - a.q_epoch < 0 && ++spins < (1 << 22)) __nanosleep(64);
+      }
+    }
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
 #define AT_TRACE(ev) do { if (a.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 1000)) a.trace[3072 + (blockIdx.x ? 8 : 0) + (ev)] = clock64(); } while (0)
   AT_TRACE(0);
   int klen = a.kbase + a.klen_src[b];

@@ -37,6 +37,10 @@ struct LayerArgs {
   const float2* stats_in;   // null: yf holds final values
   const float *pg, *pbe;
   float2* stats_out;        // null: this kernel writes y itself
+  // tile-granular hand-off to the next kernel of the stream (attn.cu, AttnArgs::q_flags): tile_flags[t] = flag_epoch
+  // is released once every global store of tile t has been issued behind a CTA barrier; null = not published
+  int* tile_flags;
+  int flag_epoch;
   bf16* out_b;       // bf16(y) [M][256] row-major or null
   bf16* out_pb;      // bf16(y + pos) [M][256] or null
   const float* pos;  // pos_mod == 0: tile-blocked per-row table ; > 0: row-major [pos_mod][256] ; null = 0
@@ -52,6 +56,7 @@ struct LayerArgs {
 };
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
                  const LayerArgs& args);
+int layer_tile_rows(int M);   // rows a layer-kernel tile advances by for a stream of M rows
 
 // fp32 tile-blocked rows -> row-major fp32: dst[(b * rows_out + j)][256] = src row (b * rows_in + j), j < rows_out
 int launch_unblock(cudaStream_t st, const float* src_blk, float* dst, int B, int rows_in, int rows_out);
@@ -80,6 +85,12 @@ struct AttnArgs {
   int v_first;              // keys < v_first contribute no value (the dummy tokens, crossattention.py:385-386)
   float* tsum;              // optional fp32 [8][B*Lq] (this layer's slot): probability mass on keys >= v_first
   long long* trace;         // debug: clock64 stamps of CTA 0 / CTA 1000 at +3072 (fvtg_dbg_set_trace)
+  // q (and nothing else this kernel reads) comes from the layer kernel launched just before, which publishes its
+  // 128-row tiles one by one (LayerArgs::tile_flags): a CTA then waits only for the tiles that hold its video's
+  // query rows instead of the whole grid, so it runs on the SMs the producer's last wave leaves idle.  null = off.
+  const int* q_flags;
+  int q_epoch;
+  int q_tile_rows;
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
 // attn_tc.cu: the same contract on tcgen05 / TMEM (one CTA per video x 128-query block x head pair)

@@ -401,6 +401,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tmem_st_wait();
       if (tr) LK_TRACE(1, 2);
       epi_bar_sync();
+      // every epilogue thread has issued the previous tile's last global stores before this barrier: publish it
+      if (g.tile_flags && it > 0 && warp == 4 && lane == 0)
+        st_release_gpu(g.tile_flags + (tile - static_cast<int>(gridDim.x)), g.flag_epoch);
       float mean, rstd;
       {
         const float2 a0 = s_stat[r], a1 = s_stat[128 + r], a2 = s_stat[256 + r], a3 = s_stat[384 + r];
@@ -603,6 +606,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       if (tr) LK_TRACE(1, 22);
     }
+    if (g.tile_flags && it > 0) {   // the CTA's last tile
+      epi_bar_sync();
+      if (warp == 4 && lane == 0)
+        st_release_gpu(g.tile_flags + (static_cast<int>(blockIdx.x) + (it - 1) * static_cast<int>(gridDim.x)), g.flag_epoch);
+    }
   }
 
   tc_fence_before();
@@ -617,6 +625,20 @@ layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+}
+
+// Tiles advance by tile_rows rows (default 128).  FVTG_LAYER_TILE_ROWS=0 picks the size that gives every
+// SM the same number of tiles (76 800 rows on 148 SMs: 5 x 104 rows instead of 4.05 -> 5 rounds of 128).
+// Measured: no gain (1.656 vs 1.638 ms/step for the 11 launches) - a tile's cost does not shrink with its
+// live rows (M = 128 MMAs, epilogue threads of dead rows still walk the phases), so it stays off.
+int layer_tile_rows(int M) {
+  static const int forced = [] { const char* e = getenv("FVTG_LAYER_TILE_ROWS"); return e ? atoi(e) : 128; }();
+  int tr = forced;
+  if (forced == 0) {
+    const int per_sm = (M + sm_count() * 128 - 1) / (sm_count() * 128);
+    tr = ((M + sm_count() * per_sm - 1) / (sm_count() * per_sm) + 7) & ~7;
+  }
+  return tr < 8 ? 8 : (tr > 128 ? 128 : (tr & ~7));
 }
 
 int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w1, const bf16* w2,
@@ -634,19 +656,7 @@ int launch_layer(cudaStream_t st, const bf16* att, const bf16* wo, const bf16* w
   FVTG_TRY(make_tmap_bf16(&tw1, w1, 1024, 256, 256, 128, 64));
   FVTG_TRY(make_tmap_bf16(&tw2, w2, 256, 1024, 1024, 256, 64));
   LayerArgs a2 = args;
-  // Tiles advance by tile_rows rows (default 128).  FVTG_LAYER_TILE_ROWS=0 picks the size that gives every
-  // SM the same number of tiles (76 800 rows on 148 SMs: 5 x 104 rows instead of 4.05 -> 5 rounds of 128).
-  // Measured: no gain (1.656 vs 1.638 ms/step for the 11 launches) - a tile's cost does not shrink with its
-  // live rows (M = 128 MMAs, epilogue threads of dead rows still walk the phases), so it stays off.
-  {
-    static const int forced = [] { const char* e = getenv("FVTG_LAYER_TILE_ROWS"); return e ? atoi(e) : 128; }();
-    int tr = forced;
-    if (forced == 0) {
-      const int per_sm = (args.M + sm_count() * 128 - 1) / (sm_count() * 128);
-      tr = ((args.M + sm_count() * per_sm - 1) / (sm_count() * per_sm) + 7) & ~7;
-    }
-    a2.tile_rows = tr < 8 ? 8 : (tr > 128 ? 128 : (tr & ~7));
-  }
+  a2.tile_rows = layer_tile_rows(args.M);
   const int tiles = (args.M + a2.tile_rows - 1) / a2.tile_rows;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   {
