@@ -485,6 +485,45 @@ torch.save({"sal": r.saliency.cpu(), "cls": r.cls_logit.cpu(), "coord": r.coord.
         assert e < TOL, f"{k}: tcgen05 attention vs default max-norm rel err {e:.3e}"
 
 
+def test_tile_handoff_is_bit_identical_to_the_grid_wide_dependency():
+    """The per-tile release/acquire between a T2V layer kernel and the next attention (FVTG_TILE_HANDOFF, default on)
+    only changes WHEN an attention CTA may start: every output must equal the grid-wide griddepcontrol.wait chain bit
+    for bit - at a size where every layer-kernel CTA owns several tiles (600 tiles on 148 SMs), twice in a row on the
+    same workspace (stale flags of the previous forward must not satisfy the next one), ragged lengths."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from flashvtg_b200 import synth
+from flashvtg_b200.config import PRESETS
+from flashvtg_b200.model import FlashVTGB200
+cfg = PRESETS["qvh_iv2"]
+m = FlashVTGB200(cfg).eval(); m.load_state_dict(synth.make_state_dict(cfg, 2025, spread=True))
+b = synth.make_inputs(cfg, 64, 75, 32, seed=12, ragged=True, min_lv=9)
+dev = torch.device("cuda:0")
+d = {k: v.repeat(16, *([1] * (v.dim() - 1))).contiguous().to(dev) for k, v in b.items()}
+out = []
+for _ in range(2):
+    r = m.infer(d["src_vid"], d["vid_len"], d["src_txt"], d["txt_len"], duration=d["duration"], want_heads=True)
+    torch.cuda.synchronize()
+    out.append({"sal": r.saliency.cpu(), "cls": r.cls_logit.cpu(), "coord": r.coord.cpu(), "t2v": r.t2vattn.cpu(),
+                "win": r.windows.cpu()})
+for k in out[0]:
+    assert torch.equal(out[0][k], out[1][k]), k
+torch.save(out[1], sys.argv[1])
+''' % ROOT
+    import tempfile
+    outs = []
+    for on in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, FVTG_TILE_HANDOFF=on)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            outs.append(torch.load(f.name))
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), f"{k}: tile hand-off changed the result"
+
+
 def test_uniform_length_hint_changes_nothing():
     """FvtgBatch.uniform_vid_len (compact sine table for chunks whose videos share one length) is a
     pure layout optimisation: bit-identical outputs with and without the hint, full and short length."""
