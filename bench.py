@@ -281,7 +281,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short watchdog: a mismatched collective must fail the run in two minutes, not hold 8 GPUs for ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
     cfg = PRESETS[args.preset]
     B_PER_GPU, LV, LT, _ = WORKLOADS[args.preset]
@@ -337,8 +339,10 @@ def run_ours(args):
             pg.wait(pg.gather(r.packed))   # next step's kernels wait only for the slot they will overwrite
         elif world > 1:
             from flashvtg_b200.distributed import gather_records
+            # bucketed shards differ in size AND in their own padded length: saliency is padded to the global one
             gather_records({"nms_windows": r.nms_windows, "count": r.count, "saliency": r.saliency},
-                           world * B_PER_GPU, plan=shard_plan(full["vid_len"], world, args.shard))
+                           world * B_PER_GPU, plan=shard_plan(full["vid_len"], world, args.shard),
+                           pad_last={"nms_windows": 3, "saliency": LV})
         return r
 
     def barrier():

@@ -7,7 +7,7 @@ NVLink on GPUs; the same code runs on gloo for the CPU tests of the host logic).
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Optional, Dict, Tuple
 
 import torch
 import torch.distributed as dist
@@ -116,13 +116,19 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int, mode: str
     return out
 
 
-def gather_records(local: Dict[str, torch.Tensor], n_total: int, group=None, plan=None) -> Dict[str, torch.Tensor]:
+def gather_records(local: Dict[str, torch.Tensor], n_total: int, group=None, plan=None,
+                   pad_last: Optional[Dict[str, int]] = None) -> Dict[str, torch.Tensor]:
     """All-gather per-video result tensors (leading dim = local shard) into global order with ONE collective.
 
     Every field's rows are viewed as bytes and laid side by side in one [max_shard][row_bytes] record buffer
     (shards padded to the largest one), a single all_gather_into_tensor moves it, and the fields are cut back
     out.  `plan` (shard_plan(...)) restores the input order of a non-contiguous split; default: contiguous.
-    Returns tensors with leading dim n_total on every rank."""
+    Returns tensors with leading dim n_total on every rank.
+
+    Ranks that cropped their shard to their own longest video (shard_batch(crop=True), the bucketed / balanced
+    plans) hold per-clip fields of different widths (saliency [n, Lv_rank]); an all-gather needs equal records, so
+    the last dim of every field is zero-padded to a common size first: `pad_last[name]` when the caller knows it
+    (no extra traffic), otherwise the maximum over the ranks (one small all_reduce)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = [shard_range(n_total, r, world) for r in range(world)] if plan is None else None
@@ -130,6 +136,21 @@ def gather_records(local: Dict[str, torch.Tensor], n_total: int, group=None, pla
     max_shard = max(max(counts), 1)
     names = list(local)
     dev = local[names[0]].device
+    last = torch.tensor([(local[k].shape[-1] if local[k].dim() > 1 else 1) for k in names], dtype=torch.int64)
+    if pad_last is not None and all(k in pad_last for k in names if local[k].dim() > 1):
+        want = torch.tensor([(pad_last[k] if local[k].dim() > 1 else 1) for k in names], dtype=torch.int64)
+        assert bool((want >= last).all()), "pad_last smaller than a local field"
+    else:
+        want = last.to(dev)
+        dist.all_reduce(want, op=dist.ReduceOp.MAX, group=group)
+        want = want.cpu()
+    padded = {}
+    for i, k in enumerate(names):
+        t = local[k]
+        if t.dim() > 1 and int(want[i]) > t.shape[-1]:
+            t = torch.nn.functional.pad(t, (0, int(want[i]) - t.shape[-1]))
+        padded[k] = t
+    local = padded
     cols, metas = [], []
     for k in names:
         t = local[k].contiguous()

@@ -46,6 +46,19 @@ def _worker_plan(rank, world, port, n_total, mode, q):
         res = {"score": local["vid_len"].float() * 2 + 1, "tag": local["txt_len"].to(torch.int32) + 5}
         got = gather_records(res, n_total, plan=plan)
         ok = ok and torch.equal(got["score"], vlen.float() * 2 + 1) and torch.equal(got["tag"], full["txt_len"] + 5)
+        # per-clip field whose width is the shard's own longest video (saliency [n, Lv_rank]): ranks of a cropped plan
+        # hold DIFFERENT widths - the records must be padded to a common one before the collective (an unequal
+        # all_gather_into_tensor hangs NCCL and gloo alike; it did, on the 8-GPU bucketed bench), with and without
+        # the caller's hint
+        sal_full = full["src_vid"][:, :, 0] * (torch.arange(75)[None, :] < vlen[:, None])
+        res2 = {"saliency": local["src_vid"][:, :, 0] * (torch.arange(local["src_vid"].shape[1])[None, :] <
+                                                            local["vid_len"][:, None]),
+                "count": local["vid_len"]}
+        for hint in (None, {"saliency": 75}):
+            got2 = gather_records(res2, n_total, plan=plan, pad_last=hint)
+            w = got2["saliency"].shape[1]
+            ok = ok and w <= 75 and torch.equal(got2["saliency"], sal_full[:, :w]) and \
+                bool((sal_full[:, w:] == 0).all()) and torch.equal(got2["count"], vlen)
         # packed fast path: equal shards, one collective, views [world][B_local][...]
         m = _StubModel()
         B, Lv = 4, 9
