@@ -282,8 +282,8 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        # a short watchdog: a mismatched collective must fail the run in two minutes, not hold 8 GPUs for ten
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        # a short watchdog: a mismatched collective must fail the run in five minutes, not hold 8 GPUs for ten or more
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     cfg = PRESETS[args.preset]
     B_PER_GPU, LV, LT, _ = WORKLOADS[args.preset]
