@@ -45,14 +45,19 @@ attn_video_kernel(const AttnArgs a, const int LqPad) {
   const int g = lane >> 2, t = lane & 3;
   pdl_launch_dependents();
   if (a.q_flags) {
-    // tile-granular dependency on the producing layer kernel (see AttnArgs::q_flags).  The spin is bounded: a
-    // protocol error shows up as a parity failure, never as a hung GPU.
+    // tile-granular dependency on the producing layer kernel (see AttnArgs::q_flags).  The spin is bounded, and a
+    // CTA that runs out of patience falls back to the grid-wide wait: never a wrong result, never a hung GPU.
     if (tid == 0) {
       const int t0 = (b * a.Lq) / a.q_tile_rows, t1 = (b * a.Lq + a.Lq - 1) / a.q_tile_rows;
-      for (int t = t0; t <= t1; ++t) {
+      bool late = false;
+      for (int t = t0; t <= t1 && !late; ++t) {
         int spins = 0;
-        while (ld_acquire_gpu(a.q_flags + t) - a.q_epoch < 0 && ++spins < (1 << 22)) __nanosleep(64);
+        while (ld_acquire_gpu(a.q_flags + t) - a.q_epoch < 0) {
+          if (++spins >= (1 << 22)) { late = true; break; }
+          __nanosleep(64);
+        }
       }
+      if (late) pdl_wait();
     }
     __syncthreads();
   } else {
